@@ -1,0 +1,129 @@
+/*
+ * nqb.h -- C ABI of the B200-native NequIP hot path (libnqb.so).
+ *
+ * Plain C: raw device pointers, sizes, a CUDA stream.  No torch / C++ types cross
+ * this boundary.  Every tensor is caller-allocated (torch caching allocator on the
+ * Python side) and only borrowed for the stream-ordered duration of the call; the
+ * library never allocates device memory per call and never synchronises the
+ * device.  All functions return 0 on success; otherwise nqb_last_error() holds a
+ * thread-local message (the Python wrapper raises RuntimeError, in the style of
+ * the reference's modifiers, nequip/nn/_tp_scatter_base.py:57-58).
+ *
+ * Reference interfaces these entry points replace (paths under /root/reference):
+ *   nqb_tp_scatter_fwd/bwd  TensorProductScatter.forward + its autograd
+ *                           nequip/nn/_tp_scatter_base.py:35-38
+ *                           (e3nn o3.TensorProduct 'uvu' + nequip/nn/utils.py:24-53 scatter;
+ *                            same seat as OpenEquivariance's TensorProductConv,
+ *                            nequip/nn/_tp_scatter_oeq.py:29-57, and cuEquivariance's
+ *                            fused_tp, nequip/nn/_tp_scatter_cueq.py:90-122)
+ *   nqb_plan_create         TensorProductScatter.__init__  nequip/nn/_tp_scatter_base.py:10-33
+ *                           (path table built at nequip/nn/interaction_block.py:89-116)
+ *   nqb_csr_*               the (dst,src)-sorted edge contract of
+ *                           nequip/data/transforms/neighborlist.py:120-157
+ *   nqb_edge_embed_fwd/bwd  with_edge_vectors_  nequip/nn/utils.py:68-118,
+ *                           SphericalHarmonicEdgeAttrs.forward  nequip/nn/embedding/_edge.py:193-198,
+ *                           EdgeLengthNormalizer :65-80, BesselEdgeLengthEncoding :136-150,
+ *                           PolynomialCutoff  nequip/nn/embedding/cutoffs.py:17-27,
+ *                           ApplyFactor  nequip/nn/misc.py:46-48
+ *   nqb_sh_fwd/bwd          e3nn o3.SphericalHarmonics(normalize=True, "component") as
+ *                           constructed at nequip/nn/embedding/_edge.py:187-189
+ */
+#ifndef NQB_H
+#define NQB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* nqb_stream_t; /* == cudaStream_t */
+typedef struct nqb_plan nqb_plan;
+
+typedef struct nqb_irrep {
+  int32_t mul;
+  int32_t l;
+  int32_t p; /* +1 even, -1 odd */
+} nqb_irrep;
+
+typedef struct nqb_instruction {
+  int32_t i_in1;
+  int32_t i_in2;
+  int32_t i_out; /* 'uvu', has_weight=True */
+} nqb_instruction;
+
+enum { NQB_F32 = 0, NQB_F64 = 1 };
+
+/* library / error handling */
+int nqb_abi_version(void);
+const char* nqb_last_error(void);
+
+/* Plan: immutable description of one TensorProductScatter signature bound to the
+ * specialised kernel library generated for it (spec_lib_path, built by
+ * nequip_b200.build; its embedded signature string is validated against the
+ * descriptors).  Thread-safe to share between the forward and autograd threads. */
+int nqb_plan_create(const nqb_irrep* in1, int n_in1, const nqb_irrep* in2, int n_in2,
+                    const nqb_irrep* out, int n_out, const nqb_instruction* ins, int n_ins,
+                    const char* spec_lib_path, nqb_plan** plan);
+void nqb_plan_destroy(nqb_plan* plan);
+int nqb_plan_dims(const nqb_plan* plan, int* d_in, int* s_dim, int* weight_numel, int* d_out);
+/* writes the canonical signature (NUL terminated) into buf; returns needed length */
+int nqb_plan_signature(const nqb_plan* plan, char* buf, int buflen);
+
+/* Destination-CSR helpers.  edge_dst must be non-decreasing for
+ * nqb_csr_from_sorted (the reference's neighbour lists are grouped by centre atom);
+ * nqb_csr_check_sorted writes 1/0 into *flag_dev.  For unsorted edges the caller
+ * supplies perm (stable argsort of edge_dst) and the sorted keys. */
+int nqb_csr_check_sorted(const int64_t* keys, int64_t E, int32_t* flag_dev, nqb_stream_t st);
+int nqb_csr_from_sorted(const int64_t* sorted_keys, int64_t E, int64_t N, int64_t* row_ptr /* [N+1] */,
+                        nqb_stream_t st);
+
+/* out[N, D_mid] = scatter_dst( TP_uvu( x[src], y, w ) ).  Every element of out is
+ * written exactly once (no pre-zeroing needed, deterministic).
+ *   x [N, D_in], y [E, S], w [E, W], out [N, D_mid]: dtype NQB_F32/NQB_F64, row-major, mul_ir layout
+ *   row_ptr [N+1]: CSR over edges ordered by destination; perm [E] or NULL (identity):
+ *   slot s of the CSR refers to edge perm[s]; src [E]: source node of each edge (original order). */
+int nqb_tp_scatter_fwd(const nqb_plan* plan, int dtype, const void* x, const void* y, const void* w,
+                       const int64_t* row_ptr, const int64_t* perm, const int64_t* src, int64_t N,
+                       int64_t E, void* out, nqb_stream_t st);
+
+/* Gradients of the above.  grad_w [E, W] is fully written.  grad_y [E, S] and
+ * grad_x [N, D_in] are ACCUMULATED INTO (caller zero-fills); grad_x may be NULL
+ * (skips the source-row reduction, e.g. first layer at inference). */
+int nqb_tp_scatter_bwd(const nqb_plan* plan, int dtype, const void* x, const void* y, const void* w,
+                       const int64_t* row_ptr, const int64_t* perm, const int64_t* src,
+                       const void* grad_out, int64_t N, int64_t E, void* grad_x, void* grad_y,
+                       void* grad_w, nqb_stream_t st);
+
+/* Real spherical harmonics, "component" normalisation, input normalised (lmax <= 3).
+ *   vec [E,3] f64 -> y [E,(lmax+1)^2] of out_dtype (computed in f64, then cast). */
+int nqb_sh_fwd(int lmax, const double* vec, int64_t E, int out_dtype, void* y, nqb_stream_t st);
+/*   grad_vec [E,3] f64 = J^T grad_y (includes the normalisation Jacobian); overwritten */
+int nqb_sh_bwd(int lmax, const double* vec, int64_t E, int out_dtype, const void* grad_y,
+               double* grad_vec, nqb_stream_t st);
+
+/* Fused edge geometry + embeddings:
+ *   r_ij = pos[idx1] - pos[idx0] + shift @ cell ; Y = SH(r_ij) ;
+ *   emb[:, n] = sinc(n x) n * f_cut(x) * prefactor , x = |r|/r_max, n = 1..num_bessel
+ * edge_index [2,E] i64; shift [E,3] f64 or NULL; cell [3,3] f64 (rows = lattice vectors) or NULL.
+ * Outputs: vec [E,3] f64 (kept for backward), y [E,S], emb [E,num_bessel] (out_dtype). */
+int nqb_edge_embed_fwd(int lmax, int num_bessel, double r_max, double poly_p, double prefactor,
+                       const double* pos, const int64_t* edge_index, const double* shift,
+                       const double* cell, int64_t N, int64_t E, int out_dtype, double* vec, void* y,
+                       void* emb, nqb_stream_t st);
+/* grad_pos [N,3] f64 is ACCUMULATED INTO (caller zero-fills):
+ *   g = J_Y^T grad_y + J_emb^T grad_emb ;  grad_pos[idx1] += g ; grad_pos[idx0] -= g.
+ * grad_vec [E,3] f64 (may be NULL) receives g itself (per-edge forces / virial assembly). */
+int nqb_edge_embed_bwd(int lmax, int num_bessel, double r_max, double poly_p, double prefactor,
+                       const double* vec, const int64_t* edge_index, int64_t N, int64_t E,
+                       int out_dtype, const void* grad_y, const void* grad_emb, double* grad_pos,
+                       double* grad_vec, nqb_stream_t st);
+
+/* number of kernels the library has launched in this process (bench accounting) */
+int64_t nqb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NQB_H */

@@ -1,0 +1,622 @@
+"""CUDA source generator for the fused tensor-product + scatter kernels (sm_100a).
+
+One translation unit per ``TensorProductScatter`` signature (the three irreps and
+the instruction list that ``InteractionBlock.__init__`` builds,
+``nequip/nn/interaction_block.py:89-116``).  The math being generated is the
+``uvu`` path of e3nn's ``o3.TensorProduct`` followed by ``scatter``
+(``nequip/nn/_tp_scatter_base.py:35-38``, ``nequip/nn/utils.py:24-53``):
+
+    out[dst, u, k] += coef_p * w[e, p, u] * sum_ij C_p[i, j, k] x[src, u, i] Y[e, j]
+
+Kernel design (see DESIGN.md for the roofline accounting and the measurements
+that led here):
+
+* edges are visited in destination-CSR order (``row_ptr``/``perm``); a *work item*
+  is ``(destination node, path group, channel block)`` and is owned by ONE warp,
+  which keeps the node's output accumulators in registers for the whole edge loop
+  and writes each output element exactly once -- no atomics, no ``[E, D_mid]``
+  intermediate, deterministic;
+* lane = channel pair: fp32 kernels carry two adjacent channels per lane as a
+  ``float2`` so that every multiply-accumulate is a packed ``FFMA2``/``FMUL2`` (the
+  Clebsch-Gordan constants ride along as 32-bit immediates broadcast to both
+  halves).  ``FFMA2`` does not raise the FMA-pipe peak (measured 128 FMA/clk/SM
+  either way) but halves the issue slots, which leaves room to co-issue the
+  loads/address math of the dominant ``w[e, p, :]`` stream;
+* path groups partition the *input chunks*, so every ``x[src]`` element and every
+  weight is loaded exactly once per edge, with coalesced 8-byte loads;
+* everything per-edge is register math: for each (input chunk, harmonic degree)
+  block the products ``t_ij = x_i Y_j`` are formed once and fanned out into all
+  output degrees ``l3`` through the sparse CG constants, then scaled by the path
+  weight into the accumulators.  (A shared-memory ``M = C.Y`` formulation was
+  measured first: broadcast ``LDS.128`` issues at 0.5/clk/SM on B200, which caps it
+  at ~60% of the FMA peak -- tools/microbench/pipes.cu.)
+* when a node has fewer channel pairs than lanes (mul < 64) the warp works on
+  ``EPW = 32 / lanes_per_edge`` edges of the node at once and folds the partial
+  accumulators with shuffles at the end;
+* the backward kernel has the same decomposition with ``grad_out[dst]`` resident in
+  registers; it writes ``grad_w`` once, reduces ``grad_Y`` over the lanes of an edge
+  and adds ``grad_x`` into the source rows with ``red.global.add``.
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass, field
+from math import sqrt
+from typing import Dict, List, Tuple
+
+from . import cg
+from .irreps import Irreps
+
+CODEGEN_VERSION = 4
+
+
+# ---------------------------------------------------------------------------
+# signature
+# ---------------------------------------------------------------------------
+@dataclass
+class Path:
+    idx: int
+    i1: int
+    i2: int
+    io: int
+    l1: int
+    l2: int
+    l3: int
+    mul: int
+    xoff: int
+    yoff: int
+    ooff: int
+    woff: int
+    coef: float
+
+
+@dataclass
+class TPSignature:
+    irreps_in1: Irreps
+    irreps_in2: Irreps
+    irreps_out: Irreps
+    instructions: List[Tuple[int, int, int]]
+    paths: List[Path] = field(default_factory=list)
+
+    def __post_init__(self):
+        self.irreps_in1 = Irreps(self.irreps_in1)
+        self.irreps_in2 = Irreps(self.irreps_in2)
+        self.irreps_out = Irreps(self.irreps_out)
+        ins = []
+        for t in self.instructions:
+            t = tuple(t)
+            if len(t) >= 5:
+                if t[3] != "uvu" or not t[4]:
+                    raise NotImplementedError(f"only weighted 'uvu' instructions are supported, got {t}")
+            ins.append((int(t[0]), int(t[1]), int(t[2])))
+        if not ins:
+            raise ValueError("empty instruction list")
+        self.instructions = ins
+        in1, in2, out = self.irreps_in1, self.irreps_in2, self.irreps_out
+        xo, yo, oo = in1.offsets(), in2.offsets(), out.offsets()
+        # element path normalisation, component irrep normalisation (e3nn defaults):
+        # alpha = dim(ir_out) / sum_{paths into the same i_out} mul_in2
+        woff = 0
+        self.paths = []
+        for idx, (i1, i2, io) in enumerate(ins):
+            mul1, ir1 = in1[i1]
+            mul2, ir2 = in2[i2]
+            mulo, iro = out[io]
+            if mul2 != 1:
+                raise NotImplementedError("edge attributes with multiplicity > 1 are not supported")
+            if mulo != mul1:
+                raise ValueError(f"'uvu' needs mul_out == mul_in1 (instruction {idx})")
+            if iro not in ir1 * ir2:
+                raise ValueError(f"instruction {idx}: {ir1} x {ir2} does not contain {iro}")
+            fan = sum(in2[j2][0] for (_, j2, jo) in ins if jo == io)
+            coef = sqrt(iro.dim / fan)
+            self.paths.append(
+                Path(idx, i1, i2, io, ir1.l, ir2.l, iro.l, mul1, xo[i1], yo[i2], oo[io], woff, coef)
+            )
+            woff += mul1 * mul2
+        self.weight_numel = woff
+        self.written_outs = sorted({p.io for p in self.paths})
+
+    @property
+    def d_in(self) -> int:
+        return self.irreps_in1.dim
+
+    @property
+    def s_dim(self) -> int:
+        return self.irreps_in2.dim
+
+    @property
+    def d_out(self) -> int:
+        return self.irreps_out.dim
+
+    def canonical(self) -> str:
+        def irs(irr):
+            return "+".join(f"{m}x{ir.l}{'e' if ir.p == 1 else 'o'}" for m, ir in irr)
+
+        ins = ";".join(f"{a},{b},{c}" for a, b, c in self.instructions)
+        return f"in1={irs(self.irreps_in1)}|in2={irs(self.irreps_in2)}|out={irs(self.irreps_out)}|ins={ins}"
+
+    def key(self, opts: "GenOptions") -> str:
+        h = hashlib.sha1((self.canonical() + "|" + opts.tag() + f"|v{CODEGEN_VERSION}").encode()).hexdigest()
+        return h[:16]
+
+    def fma_count(self) -> int:
+        """Multiply-accumulates per (edge, channel) of the generated forward math."""
+        n = 0
+        blocks: Dict[Tuple[int, int], List[Path]] = {}
+        for p in self.paths:
+            blocks.setdefault((p.i1, p.i2), []).append(p)
+        for (_, _), ps in blocks.items():
+            l1, l2 = ps[0].l1, ps[0].l2
+            if l2 == 0:
+                n += sum(2 + (2 * p.l3 + 1) for p in ps)
+                continue
+            supp = set()
+            for p in ps:
+                for (i, j, k, _c) in cg.sparse_w3j(p.l1, p.l2, p.l3):
+                    supp.add((i, j))
+                    n += 1
+                n += 2 * p.l3 + 1
+            n += len(supp)
+        return n
+
+
+@dataclass
+class GenOptions:
+    nwarp: int = 4  # warps (= destination nodes) per CTA
+    acc_cap: int = 32  # max output components per channel held by one warp (forward)
+    acc_cap_bwd: int = 24
+    prefetch: bool = False
+
+    def tag(self) -> str:
+        return f"w{self.nwarp}_a{self.acc_cap}_b{self.acc_cap_bwd}_p{int(self.prefetch)}"
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+class _Emitter:
+    def __init__(self):
+        self.lines: List[str] = []
+        self.ind = 0
+
+    def __call__(self, s: str = ""):
+        self.lines.append(("  " * self.ind + s) if s else "")
+
+    def block(self, head: str = ""):
+        self((head + " {") if head else "{")
+        self.ind += 1
+
+    def end(self, tail: str = "}"):
+        self.ind -= 1
+        self(tail)
+
+    def text(self) -> str:
+        return "\n".join(self.lines) + "\n"
+
+
+def _imm(v: float) -> str:
+    return f"T({v!r})"
+
+
+def _pow2ceil(n: int) -> int:
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+def _partition(sig: TPSignature, acc_cap: int) -> List[List[Path]]:
+    """Group whole input chunks (so x and w are loaded once), keeping paths that
+    write the same output chunk together, subject to an accumulator budget."""
+    # clusters: connected components over (i1) and shared io
+    by_i1: Dict[int, List[Path]] = {}
+    for p in sig.paths:
+        by_i1.setdefault(p.i1, []).append(p)
+    parent = {i1: i1 for i1 in by_i1}
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    io_owner: Dict[int, int] = {}
+    for p in sig.paths:
+        if p.io in io_owner:
+            parent[find(p.i1)] = find(io_owner[p.io])
+        else:
+            io_owner[p.io] = p.i1
+    clusters: Dict[int, List[Path]] = {}
+    for i1, ps in by_i1.items():
+        clusters.setdefault(find(i1), []).extend(ps)
+    cl = sorted(clusters.values(), key=lambda ps: min(p.i1 for p in ps))
+
+    def ncomp(ps):
+        return sum(sig.irreps_out[io][1].dim for io in {p.io for p in ps})
+
+    groups: List[List[Path]] = []
+    cur: List[Path] = []
+    for ps in cl:
+        if cur and ncomp(cur) + ncomp(ps) > acc_cap:
+            groups.append(cur)
+            cur = []
+        cur = cur + ps
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+# ---------------------------------------------------------------------------
+# generator
+# ---------------------------------------------------------------------------
+class TPGenerator:
+    def __init__(self, sig: TPSignature, opts: GenOptions | None = None):
+        self.sig = sig
+        self.opts = opts or GenOptions()
+        self.mul_max = max(p.mul for p in sig.paths)
+        self.fwd_groups = _partition(sig, self.opts.acc_cap)
+        self.bwd_groups = _partition(sig, self.opts.acc_cap_bwd)
+
+    def geometry(self, cpt: int):
+        """lanes per edge, edges per warp iteration, channel blocks."""
+        pairs = (self.mul_max + cpt - 1) // cpt
+        lpe = min(32, _pow2ceil(pairs))
+        epw = 32 // lpe
+        cb = (pairs + lpe - 1) // lpe
+        return lpe, epw, cb
+
+    # -- per-group helpers ------------------------------------------------------
+    @staticmethod
+    def _blocks(paths: List[Path]) -> List[Tuple[Tuple[int, int], List[Path]]]:
+        b: Dict[Tuple[int, int], List[Path]] = {}
+        for p in paths:
+            b.setdefault((p.i1, p.i2), []).append(p)
+        return sorted(b.items())
+
+    def _emit_edge_prologue(self, em: _Emitter, paths: List[Path], want_valid_mask_w: bool):
+        sig = self.sig
+        S = sig.s_dim
+        em("int64_t s = s0 + sub;")
+        em("const bool valid = s < end;")
+        em("if (!valid) s = beg;")
+        em("const int64_t e = perm ? perm[s] : s;")
+        em("const int64_t sn = src[e];")
+        # harmonics of this edge, splatted over the channel vector
+        yused = sorted({p.yoff + j for p in paths for j in range(2 * p.l2 + 1)})
+        for j in yused:
+            em(f"const V y{j} = vsplat(__ldg(y + e * {S} + {j}));")
+        # x chunks
+        for i1 in sorted({p.i1 for p in paths}):
+            mul, ir = sig.irreps_in1[i1]
+            n1 = ir.dim
+            xoff = sig.irreps_in1.offsets()[i1]
+            em(f"const T* xp{i1} = x + sn * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
+            for i in range(n1):
+                em(f"const V x{i1}_{i} = vload<{n1}, {mul}>(xp{i1} + {i}, ch0);")
+        # weights
+        for p in paths:
+            zero = "valid" if want_valid_mask_w else "true"
+            al = "true" if (sig.weight_numel % 2 == 0 and p.woff % 2 == 0) else "false"
+            em(f"const V w{p.idx} = vloadw<{p.mul}, {al}>(w + e * {sig.weight_numel} + {p.woff} + ch0, ch0, {zero});")
+        return yused
+
+    # -- forward ---------------------------------------------------------------------
+    def _emit_fwd_group(self, em: _Emitter, gid: int, paths: List[Path]):
+        sig = self.sig
+        outs = sorted({p.io for p in paths})
+        em.block(
+            f"template <typename T> __device__ __forceinline__ void fwd_g{gid}("
+            "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
+            "const int64_t* __restrict__ perm, const int64_t* __restrict__ src, "
+            "int64_t n, int64_t beg, int64_t end, int ch0, int sub, T* __restrict__ out)"
+        )
+        em("typedef typename VT<T>::V V; constexpr int EPW = VT<T>::EPW; constexpr int LPE = VT<T>::LPE;")
+        for io in outs:
+            n3 = sig.irreps_out[io][1].dim
+            em("V " + ", ".join(f"a{io}_{k} = vzero<T>()" for k in range(n3)) + ";")
+        em.block("for (int64_t s0 = beg; s0 < end; s0 += EPW)")
+        self._emit_edge_prologue(em, paths, True)
+        for (i1, i2), ps in self._blocks(paths):
+            l1, l2 = ps[0].l1, ps[0].l2
+            n1 = 2 * l1 + 1
+            yoff = ps[0].yoff
+            em(f"// block in1[{i1}] (l={l1}) x in2[{i2}] (l={l2}) -> " + ", ".join(f"l3={p.l3}" for p in ps))
+            em.block()
+            if l2 == 0:
+                for p in ps:
+                    kappa = p.coef * cg.real_w3j(p.l1, 0, p.l3)[0][0][0]
+                    em(f"const V ws{p.idx} = vmul(w{p.idx}, vmuli(y{yoff}, {_imm(kappa)}));")
+                    for k in range(n1):
+                        em(f"a{p.io}_{k} = vfma(ws{p.idx}, x{i1}_{k}, a{p.io}_{k});")
+            else:
+                # sparse fan-out: t_ij -> v_p[k]
+                fan: Dict[Tuple[int, int], List[Tuple[Path, int, float]]] = {}
+                for p in ps:
+                    for (i, j, k, c) in cg.sparse_w3j(p.l1, p.l2, p.l3):
+                        fan.setdefault((i, j), []).append((p, k, p.coef * c))
+                vnames = sorted({f"v{p.idx}_{k}" for lst in fan.values() for (p, k, _c) in lst})
+                em("V " + ", ".join(vnames) + ";")
+                started = set()
+                for (i, j) in sorted(fan):
+                    em.block()
+                    em(f"const V t = vmul(x{i1}_{i}, y{yoff + j});")
+                    for (p, k, c) in fan[(i, j)]:
+                        nm = f"v{p.idx}_{k}"
+                        if nm not in started:
+                            em(f"{nm} = vmuli(t, {_imm(c)});")
+                            started.add(nm)
+                        else:
+                            em(f"{nm} = vfmai(t, {_imm(c)}, {nm});")
+                    em.end()
+                for p in ps:
+                    for k in range(2 * p.l3 + 1):
+                        if f"v{p.idx}_{k}" in started:
+                            em(f"a{p.io}_{k} = vfma(w{p.idx}, v{p.idx}_{k}, a{p.io}_{k});")
+            em.end()
+        em.end()  # edge loop
+        # fold edge sub-groups
+        em.block("if (EPW > 1)")
+        for io in outs:
+            n3 = sig.irreps_out[io][1].dim
+            for k in range(n3):
+                em(f"a{io}_{k} = vfold<LPE>(a{io}_{k});")
+        em.end()
+        em.block("if (sub == 0)")
+        for io in outs:
+            mul, ir = sig.irreps_out[io]
+            n3 = ir.dim
+            ooff = sig.irreps_out.offsets()[io]
+            em(f"T* op{io} = out + n * {sig.d_out} + {ooff} + (int64_t)ch0 * {n3};")
+            for k in range(n3):
+                em(f"vstore<{n3}, {mul}>(op{io} + {k}, a{io}_{k}, ch0);")
+        em.end()
+        em.end()
+        em()
+
+    # -- backward ---------------------------------------------------------------------
+    def _emit_bwd_group(self, em: _Emitter, gid: int, paths: List[Path]):
+        sig = self.sig
+        S = sig.s_dim
+        outs = sorted({p.io for p in paths})
+        em.block(
+            f"template <typename T, bool WANT_GX> __device__ __forceinline__ void bwd_g{gid}("
+            "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
+            "const int64_t* __restrict__ perm, const int64_t* __restrict__ src, const T* __restrict__ gout, "
+            "int64_t n, int64_t beg, int64_t end, int ch0, int sub, int cl, "
+            "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw)"
+        )
+        em("typedef typename VT<T>::V V; constexpr int EPW = VT<T>::EPW; constexpr int LPE = VT<T>::LPE;")
+        for io in outs:
+            mul, ir = sig.irreps_out[io]
+            n3 = ir.dim
+            ooff = sig.irreps_out.offsets()[io]
+            em(f"const T* gp{io} = gout + n * {sig.d_out} + {ooff} + (int64_t)ch0 * {n3};")
+            for k in range(n3):
+                em(f"const V g{io}_{k} = vload<{n3}, {mul}>(gp{io} + {k}, ch0);")
+        em.block("for (int64_t s0 = beg; s0 < end; s0 += EPW)")
+        yused = self._emit_edge_prologue(em, paths, False)
+        em("V " + ", ".join(f"q{j} = vzero<T>()" for j in yused) + ";")
+        for i1 in sorted({p.i1 for p in paths}):
+            n1 = sig.irreps_in1[i1][1].dim
+            em("V " + ", ".join(f"d{i1}_{i} = vzero<T>()" for i in range(n1)) + ";")
+        for (i1, i2), ps in self._blocks(paths):
+            l1, l2 = ps[0].l1, ps[0].l2
+            n1 = 2 * l1 + 1
+            yoff = ps[0].yoff
+            em(f"// block in1[{i1}] (l={l1}) x in2[{i2}] (l={l2})")
+            em.block()
+            if l2 == 0:
+                for p in ps:
+                    kappa = p.coef * cg.real_w3j(p.l1, 0, p.l3)[0][0][0]
+                    em(f"V r{p.idx} = vmul(x{i1}_0, g{p.io}_0);")
+                    for k in range(1, n1):
+                        em(f"r{p.idx} = vfma(x{i1}_{k}, g{p.io}_{k}, r{p.idx});")
+                    em(f"const V ky{p.idx} = vmuli(y{yoff}, {_imm(kappa)});")
+                    al = "true" if (sig.weight_numel % 2 == 0 and p.woff % 2 == 0) else "false"
+                    em(f"if (valid) vstorew<{p.mul}, {al}>(gw + e * {sig.weight_numel} + {p.woff} + ch0, vmul(ky{p.idx}, r{p.idx}), ch0);")
+                    em(f"q{yoff} = vfma(vmuli(w{p.idx}, {_imm(kappa)}), r{p.idx}, q{yoff});")
+                    em.block("if (WANT_GX)")
+                    em(f"const V ws = vmul(w{p.idx}, ky{p.idx});")
+                    for k in range(n1):
+                        em(f"d{i1}_{k} = vfma(ws, g{p.io}_{k}, d{i1}_{k});")
+                    em.end()
+            else:
+                fan: Dict[Tuple[int, int], List[Tuple[Path, int, float]]] = {}
+                for p in ps:
+                    for (i, j, k, c) in cg.sparse_w3j(p.l1, p.l2, p.l3):
+                        fan.setdefault((i, j), []).append((p, k, p.coef * c))
+                vnames = sorted({f"v{p.idx}_{k}" for lst in fan.values() for (p, k, _c) in lst})
+                em("V " + ", ".join(vnames) + ";")
+                for p in ps:
+                    for k in range(2 * p.l3 + 1):
+                        if f"v{p.idx}_{k}" in vnames:
+                            em(f"const V G{p.idx}_{k} = vmul(w{p.idx}, g{p.io}_{k});")
+                started = set()
+                for (i, j) in sorted(fan):
+                    em.block()
+                    em(f"const V t = vmul(x{i1}_{i}, y{yoff + j});")
+                    first = True
+                    for (p, k, c) in fan[(i, j)]:
+                        if first:
+                            em(f"V a = vmuli(G{p.idx}_{k}, {_imm(c)});")
+                            first = False
+                        else:
+                            em(f"a = vfmai(G{p.idx}_{k}, {_imm(c)}, a);")
+                        nm = f"v{p.idx}_{k}"
+                        if nm not in started:
+                            em(f"{nm} = vmuli(t, {_imm(c)});")
+                            started.add(nm)
+                        else:
+                            em(f"{nm} = vfmai(t, {_imm(c)}, {nm});")
+                    em(f"if (WANT_GX) d{i1}_{i} = vfma(y{yoff + j}, a, d{i1}_{i});")
+                    em(f"q{yoff + j} = vfma(x{i1}_{i}, a, q{yoff + j});")
+                    em.end()
+                for p in ps:
+                    ks = [k for k in range(2 * p.l3 + 1) if f"v{p.idx}_{k}" in vnames]
+                    em(f"V r{p.idx} = vmul(g{p.io}_{ks[0]}, v{p.idx}_{ks[0]});")
+                    for k in ks[1:]:
+                        em(f"r{p.idx} = vfma(g{p.io}_{k}, v{p.idx}_{k}, r{p.idx});")
+                    al = "true" if (sig.weight_numel % 2 == 0 and p.woff % 2 == 0) else "false"
+                    em(f"if (valid) vstorew<{p.mul}, {al}>(gw + e * {sig.weight_numel} + {p.woff} + ch0, r{p.idx}, ch0);")
+            em.end()
+        # grad_x: atomics into the source row
+        em.block("if (WANT_GX && valid)")
+        for i1 in sorted({p.i1 for p in paths}):
+            mul, ir = sig.irreps_in1[i1]
+            n1 = ir.dim
+            xoff = sig.irreps_in1.offsets()[i1]
+            em(f"T* gxp{i1} = gx + sn * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
+            for i in range(n1):
+                em(f"vatomic<{n1}, {mul}>(gxp{i1} + {i}, d{i1}_{i}, ch0);")
+        em.end()
+        # grad_Y: reduce over the lanes that share this edge, one atomic per component
+        for j in yused:
+            em(f"const T qs{j} = lane_sum<LPE>(vhsum(q{j}));")
+        em.block("if (cl == 0 && valid)")
+        for j in yused:
+            em(f"atomicAdd(gy + e * {S} + {j}, qs{j});")
+        em.end()
+        em.end()  # edge loop
+        em.end()
+        em()
+
+    # -- translation unit ----------------------------------------------------------------
+    def source(self) -> str:
+        sig = self.sig
+        em = _Emitter()
+        lpe_f, epw_f, cb_f = self.geometry(2)
+        lpe_d, epw_d, cb_d = self.geometry(1)
+        em(f"// AUTO-GENERATED by nequip_b200/codegen.py (v{CODEGEN_VERSION}) -- do not edit.")
+        em(f"// signature: {sig.canonical()}")
+        em(f"// options: {self.opts.tag()}  fwd_groups={len(self.fwd_groups)} bwd_groups={len(self.bwd_groups)}")
+        em(f"// forward multiply-accumulates per (edge, channel): {sig.fma_count()}")
+        em("#include <cuda_runtime.h>")
+        em("namespace {")
+        em(f"constexpr int NWARP = {self.opts.nwarp};")
+        em("template <typename T> struct VT;")
+        em(
+            f"template <> struct VT<float> {{ typedef float2 V; static constexpr int CPT = 2, LPE = {lpe_f}, "
+            f"EPW = {epw_f}, CB = {cb_f}; }};"
+        )
+        em(
+            f"template <> struct VT<double> {{ typedef double V; static constexpr int CPT = 1, LPE = {lpe_d}, "
+            f"EPW = {epw_d}, CB = {cb_d}; }};"
+        )
+        em(f"constexpr int NGF = {len(self.fwd_groups)};")
+        em(f"constexpr int NGB = {len(self.bwd_groups)};")
+        em("}  // namespace")
+        em('#include "nqb_tp_device.cuh"')
+        em("namespace {")
+        em()
+        for gid, ps in enumerate(self.fwd_groups):
+            self._emit_fwd_group(em, gid, ps)
+        for gid, ps in enumerate(self.bwd_groups):
+            self._emit_bwd_group(em, gid, ps)
+        # unwritten output chunks (irreps_out entries no instruction writes) must be zero-filled
+        unwritten = [io for io in range(len(sig.irreps_out)) if io not in sig.written_outs]
+        # kernels
+        em.block(
+            "template <typename T> __global__ void __launch_bounds__(32 * NWARP) tp_fwd_kernel("
+            "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
+            "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
+            "const int64_t* __restrict__ src, int64_t N, T* __restrict__ out)"
+        )
+        em("constexpr int CB = VT<T>::CB, LPE = VT<T>::LPE, CPT = VT<T>::CPT;")
+        em("const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
+        em("const int64_t n = (int64_t)blockIdx.x * NWARP + warp;")
+        em("if (n >= N) return;")
+        em("const int grp = blockIdx.y / CB, cb = blockIdx.y % CB;")
+        em("const int sub = lane / LPE, cl = lane % LPE;")
+        em("const int ch0 = (cb * LPE + cl) * CPT;")
+        em("const int64_t beg = row_ptr[n], end = row_ptr[n + 1];")
+        em.block("switch (grp)")
+        for gid in range(len(self.fwd_groups)):
+            em(f"case {gid}: fwd_g{gid}<T>(x, y, w, perm, src, n, beg, end, ch0, sub, out); break;")
+        em("default: break;")
+        em.end()
+        if unwritten:
+            em.block("if (blockIdx.y == 0)")
+            for io in unwritten:
+                mul, ir = sig.irreps_out[io]
+                ooff = sig.irreps_out.offsets()[io]
+                em(f"for (int q = lane; q < {mul * ir.dim}; q += 32) out[n * {sig.d_out} + {ooff} + q] = T(0);")
+            em.end()
+        em.end()
+        em()
+        em.block(
+            "template <typename T, bool WANT_GX> __global__ void __launch_bounds__(32 * NWARP) tp_bwd_kernel("
+            "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
+            "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
+            "const int64_t* __restrict__ src, const T* __restrict__ gout, int64_t N, "
+            "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw)"
+        )
+        em("constexpr int CB = VT<T>::CB, LPE = VT<T>::LPE, CPT = VT<T>::CPT;")
+        em("const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
+        em("const int64_t n = (int64_t)blockIdx.x * NWARP + warp;")
+        em("if (n >= N) return;")
+        em("const int grp = blockIdx.y / CB, cb = blockIdx.y % CB;")
+        em("const int sub = lane / LPE, cl = lane % LPE;")
+        em("const int ch0 = (cb * LPE + cl) * CPT;")
+        em("const int64_t beg = row_ptr[n], end = row_ptr[n + 1];")
+        em.block("switch (grp)")
+        for gid in range(len(self.bwd_groups)):
+            em(
+                f"case {gid}: bwd_g{gid}<T, WANT_GX>(x, y, w, perm, src, gout, n, beg, end, ch0, sub, cl, "
+                "gx, gy, gw); break;"
+            )
+        em("default: break;")
+        em.end()
+        em.end()
+        em("}  // namespace")
+        em()
+        # C entry points
+        em(f'extern "C" const char* nqb_spec_signature() {{ return "{sig.canonical()}"; }}')
+        em(f'extern "C" int nqb_spec_version() {{ return {CODEGEN_VERSION}; }}')
+        em(
+            'extern "C" int nqb_spec_dims(int* d_in, int* s_dim, int* w_numel, int* d_out) '
+            f"{{ *d_in = {sig.d_in}; *s_dim = {sig.s_dim}; *w_numel = {sig.weight_numel}; *d_out = {sig.d_out}; return 0; }}"
+        )
+        em.block(
+            'extern "C" int nqb_spec_fwd(int dtype, const void* x, const void* y, const void* w, '
+            "const int64_t* row_ptr, const int64_t* perm, const int64_t* src, int64_t N, int64_t E, "
+            "void* out, cudaStream_t st)"
+        )
+        em("(void)E;")
+        em("if (N <= 0) return 0;")
+        em("dim3 block(32 * NWARP);")
+        em.block("if (dtype == 0)")
+        em("dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGF * VT<float>::CB);")
+        em("tp_fwd_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, N, (float*)out);")
+        em.end()
+        em.block("else")
+        em("dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGF * VT<double>::CB);")
+        em("tp_fwd_kernel<double><<<grid, block, 0, st>>>((const double*)x, (const double*)y, (const double*)w, row_ptr, perm, src, N, (double*)out);")
+        em.end()
+        em("return (int)cudaGetLastError();")
+        em.end()
+        em.block(
+            'extern "C" int nqb_spec_bwd(int dtype, const void* x, const void* y, const void* w, '
+            "const int64_t* row_ptr, const int64_t* perm, const int64_t* src, const void* gout, "
+            "int64_t N, int64_t E, void* gx, void* gy, void* gw, cudaStream_t st)"
+        )
+        em("(void)E;")
+        em("if (N <= 0) return 0;")
+        em("dim3 block(32 * NWARP);")
+        for dt, name in ((0, "float"), (1, "double")):
+            em.block(f"if (dtype == {dt})")
+            em(f"dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGB * VT<{name}>::CB);")
+            args = (
+                f"(const {name}*)x, (const {name}*)y, (const {name}*)w, row_ptr, perm, src, "
+                f"(const {name}*)gout, N, ({name}*)gx, ({name}*)gy, ({name}*)gw"
+            )
+            em(f"if (gx) tp_bwd_kernel<{name}, true><<<grid, block, 0, st>>>({args});")
+            em(f"else tp_bwd_kernel<{name}, false><<<grid, block, 0, st>>>({args});")
+            em.end()
+        em("return (int)cudaGetLastError();")
+        em.end()
+        return em.text()
+
+
+def generate(sig: TPSignature, opts: GenOptions | None = None) -> str:
+    return TPGenerator(sig, opts).source()

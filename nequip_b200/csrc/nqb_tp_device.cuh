@@ -1,0 +1,133 @@
+// Device-side vocabulary shared by every generated tensor-product kernel
+// (nequip_b200/codegen.py).  fp32 kernels work on channel PAIRS held in a float2 so
+// that all arithmetic is packed FFMA2 / FMUL2 (sm_100a); fp64 kernels are scalar.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+// ---- lane geometry traits are emitted per signature: VT<T>::{V, CPT, LPE, EPW, CB}
+template <typename T> struct VT;
+
+// ---- construction ---------------------------------------------------------------
+__device__ __forceinline__ float2 vsplat(float a) { return make_float2(a, a); }
+__device__ __forceinline__ double vsplat(double a) { return a; }
+template <typename T> __device__ __forceinline__ typename VT<T>::V vzero();
+template <> __device__ __forceinline__ float2 vzero<float>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ double vzero<double>() { return 0.0; }
+
+// ---- arithmetic -----------------------------------------------------------------
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// immediate forms: the constant is broadcast to both halves (FFMA2 R, R.F32x2, imm, R)
+__device__ __forceinline__ float2 vmuli(float2 a, float c) { return __fmul2_rn(a, make_float2(c, c)); }
+__device__ __forceinline__ float2 vfmai(float2 a, float c, float2 b) { return __ffma2_rn(a, make_float2(c, c), b); }
+__device__ __forceinline__ double vmul(double a, double b) { return a * b; }
+__device__ __forceinline__ double vfma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ double vmuli(double a, double c) { return a * c; }
+__device__ __forceinline__ double vfmai(double a, double c, double b) { return fma(a, c, b); }
+__device__ __forceinline__ float vhsum(float2 a) { return a.x + a.y; }
+__device__ __forceinline__ double vhsum(double a) { return a; }
+
+// ---- strided channel loads: component i of CPT adjacent channels ---------------------
+// p points at (channel ch0, component i); the next channel is N elements further.
+template <int N, int MUL> __device__ __forceinline__ float2 vload(const float* __restrict__ p, int ch0) {
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  if (full) return make_float2(__ldg(p), __ldg(p + N));
+  return make_float2(ch0 < MUL ? __ldg(p) : 0.f, ch0 + 1 < MUL ? __ldg(p + N) : 0.f);
+}
+template <int N, int MUL> __device__ __forceinline__ double vload(const double* __restrict__ p, int ch0) {
+  constexpr bool full = (MUL % VT<double>::LPE) == 0;
+  if (full) return __ldg(p);
+  return ch0 < MUL ? __ldg(p) : 0.0;
+}
+template <int N, int MUL> __device__ __forceinline__ void vstore(float* __restrict__ p, float2 v, int ch0) {
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  if (full || ch0 < MUL) p[0] = v.x;
+  if (full || ch0 + 1 < MUL) p[N] = v.y;
+}
+template <int N, int MUL> __device__ __forceinline__ void vstore(double* __restrict__ p, double v, int ch0) {
+  constexpr bool full = (MUL % VT<double>::LPE) == 0;
+  if (full || ch0 < MUL) p[0] = v;
+}
+template <int N, int MUL> __device__ __forceinline__ void vatomic(float* p, float2 v, int ch0) {
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  if (full || ch0 < MUL) atomicAdd(p, v.x);
+  if (full || ch0 + 1 < MUL) atomicAdd(p + N, v.y);
+}
+template <int N, int MUL> __device__ __forceinline__ void vatomic(double* p, double v, int ch0) {
+  constexpr bool full = (MUL % VT<double>::LPE) == 0;
+  if (full || ch0 < MUL) atomicAdd(p, v);
+}
+
+// ---- contiguous per-channel scalars (the radial weights): streamed, never re-read -------
+__device__ __forceinline__ float2 ld_stream2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+template <int MUL, bool AL2> __device__ __forceinline__ float2 vloadw(const float* __restrict__ p, int ch0, bool valid) {
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  float2 r;
+  if (full && AL2) {
+    r = ld_stream2(p);
+  } else {
+    r.x = (full || ch0 < MUL) ? ld_stream(p) : 0.f;
+    r.y = (full || ch0 + 1 < MUL) ? ld_stream(p + 1) : 0.f;
+  }
+  if (!valid) r = make_float2(0.f, 0.f);
+  return r;
+}
+template <int MUL, bool AL2> __device__ __forceinline__ double vloadw(const double* __restrict__ p, int ch0, bool valid) {
+  constexpr bool full = (MUL % VT<double>::LPE) == 0;
+  double r = (full || ch0 < MUL) ? ld_stream(p) : 0.0;
+  return valid ? r : 0.0;
+}
+template <int MUL, bool AL2> __device__ __forceinline__ void vstorew(float* __restrict__ p, float2 v, int ch0) {
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  if (full && AL2) {
+    *reinterpret_cast<float2*>(p) = v;
+  } else {
+    if (full || ch0 < MUL) p[0] = v.x;
+    if (full || ch0 + 1 < MUL) p[1] = v.y;
+  }
+}
+template <int MUL, bool AL2> __device__ __forceinline__ void vstorew(double* __restrict__ p, double v, int ch0) {
+  constexpr bool full = (MUL % VT<double>::LPE) == 0;
+  if (full || ch0 < MUL) p[0] = v;
+}
+
+// ---- cross-lane -----------------------------------------------------------------------
+// sum the partial accumulators of the EPW edge sub-groups (lanes l, l+LPE, l+2LPE, ...)
+template <int LPE> __device__ __forceinline__ float2 vfold(float2 a) {
+#pragma unroll
+  for (int o = LPE; o < 32; o <<= 1) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+  }
+  return a;
+}
+template <int LPE> __device__ __forceinline__ double vfold(double a) {
+#pragma unroll
+  for (int o = LPE; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+// sum over the LPE lanes that share one edge
+template <int LPE, typename T> __device__ __forceinline__ T lane_sum(T v) {
+#pragma unroll
+  for (int o = LPE / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace

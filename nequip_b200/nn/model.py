@@ -1,0 +1,380 @@
+"""Host-side (PyTorch) mirror of the NequIP energy model around the fused kernels.
+
+This is *plumbing*: the module order, irreps bookkeeping, initialisation and
+normalisation constants of the reference's model builder, so that the hot-path
+kernels can be driven end to end (energy + forces) on identical
+``AtomicDataDict``-shaped batches without e3nn/nequip installed.  Everything on the
+per-edge hot path goes through ``nequip_b200.ops`` (CUDA); node-side dense algebra
+uses torch matmul (cuBLAS, fp32, TF32 off).
+
+Reference files mirrored (under /root/reference):
+  model assembly          nequip/model/nequip_models.py:116-210 (NequIPGNNModel), :214-399 (Full...)
+  ConvNetLayer            nequip/nn/convnetlayer.py:74-170
+  InteractionBlock        nequip/nn/interaction_block.py:21-207
+  ScalarMLPFunction       nequip/nn/mlp.py:80-195, ScalarLinearLayer :223-271
+  AvgNumNeighborsNorm     nequip/nn/norm.py:7-68
+  NodeTypeEmbed           nequip/nn/embedding/node.py:146-175
+  PerTypeScaleShift       nequip/nn/atomwise.py:236-284;  AtomwiseReduce :92-113
+  ForceStressOutput       nequip/nn/grad_output.py:107-298 (forces only)
+  e3nn o3.Linear / FullyConnectedTensorProduct / nn.Gate semantics: SURVEY.md Appendix A.4
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import ops
+from ..irreps import Irrep, Irreps, build_tp_instructions, tp_path_exists
+from .tp_scatter import B200TensorProductScatter
+
+# e3nn.math.normalize2mom constants: (E_{z~N(0,1)} act(z)^2)^(-1/2) estimated from
+# torch.randn(1_000_000, generator=Generator("cpu").manual_seed(0), dtype=float64)
+C_SILU = 1.6791767923989418
+C_TANH = 1.5937334472592692
+
+# AtomicDataDict keys used here (nequip/data/_keys.py:14-115)
+POSITIONS_KEY = "pos"
+EDGE_INDEX_KEY = "edge_index"
+EDGE_CELL_SHIFT_KEY = "edge_cell_shift"
+CELL_KEY = "cell"
+ATOM_TYPE_KEY = "atom_types"
+TOTAL_ENERGY_KEY = "total_energy"
+PER_ATOM_ENERGY_KEY = "atomic_energy"
+FORCE_KEY = "forces"
+
+
+# ---------------------------------------------------------------------------------------
+# irreps bookkeeping of the conv stack
+# ---------------------------------------------------------------------------------------
+def hidden_irreps(l_max: int, num_features: int, parity: bool) -> Irreps:
+    """``feature_irreps_hidden`` of NequIPGNNModel (nequip_models.py:176-187)."""
+    items = []
+    for l in range(l_max + 1):
+        ps = (1, -1) if parity else ((1,) if l % 2 == 0 else (-1,))
+        for p in ps:
+            items.append((num_features, Irrep(l, p)))
+    return Irreps(items)
+
+
+def gate_irreps(prev: Irreps, edge_attr: Irreps, hidden: Irreps):
+    """Irreps decisions of ConvNetLayer.__init__ (convnetlayer.py:74-114) for the gate nonlinearity.
+    Returns (irreps_scalars, irreps_gates, irreps_gated, conv_irreps_out, layer_out)."""
+    scalars = Irreps([(mul, ir) for mul, ir in hidden if ir.l == 0 and tp_path_exists(prev, edge_attr, ir)])
+    gated = Irreps([(mul, ir) for mul, ir in hidden if ir.l > 0 and tp_path_exists(prev, edge_attr, ir)])
+    gate_ir = Irrep(0, 1) if tp_path_exists(prev, edge_attr, Irrep(0, 1)) else Irrep(0, -1)
+    gates = Irreps([(mul, gate_ir) for mul, _ in gated])
+    conv_out = (scalars + gates + gated).simplify()
+    # Gate.irreps_out = scalars + gated (with gates of even parity the gated irreps are unchanged)
+    gated_out = Irreps([(mul, Irrep(ir.l, ir.p * gate_ir.p)) for mul, ir in gated])
+    layer_out = scalars + gated_out
+    return scalars, gates, gated, conv_out, layer_out
+
+
+def layer_irreps(l_max: int, num_features: int, num_layers: int, parity: bool = True, type_embed_num_features=None):
+    """[(feature_irreps_in, irreps_edge_attr, conv_irreps_out, (scalars, gates, gated))] per layer."""
+    f0 = type_embed_num_features or num_features
+    edge_attr = Irreps.spherical_harmonics(l_max)
+    prev = Irreps([(f0, Irrep(0, 1))])
+    hid = hidden_irreps(l_max, num_features, parity)
+    hiddens = [hid] * (num_layers - 1) + [Irreps([(num_features, Irrep(0, 1))])]
+    out = []
+    for h in hiddens:
+        scalars, gates, gated, conv_out, layer_out = gate_irreps(prev, edge_attr, h)
+        out.append((prev, edge_attr, conv_out, (scalars, gates, gated)))
+        prev = layer_out
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# dense pieces (torch)
+# ---------------------------------------------------------------------------------------
+class ScalarLinearLayer(torch.nn.Module):
+    """mlp.py:223-271: ``mm(input, weight * alpha)``, weight ~ U(-sqrt3, sqrt3)."""
+
+    def __init__(self, in_features: int, out_features: int, alpha: float = 1.0):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.register_buffer("alpha", torch.tensor(alpha), persistent=False)
+        self.weight = torch.nn.Parameter(torch.empty((in_features, out_features)))
+        torch.nn.init.uniform_(self.weight, -math.sqrt(3), math.sqrt(3))
+
+    def forward(self, x):
+        return torch.mm(x, self.weight * self.alpha)
+
+
+class ScalarMLPFunction(torch.nn.Module):
+    """mlp.py:80-195 with ``bias=False, forward_weight_init=True, nonlinearity="silu"``."""
+
+    def __init__(self, input_dim: int, output_dim: int, hidden_layers_depth: int = 0,
+                 hidden_layers_width: Optional[int] = None, nonlinearity: Optional[str] = "silu"):
+        super().__init__()
+        dims = [input_dim] + hidden_layers_depth * [hidden_layers_width] + [output_dim]
+        self.dims = dims
+        layers: List[torch.nn.Module] = []
+        nl = len(dims) - 1
+        for layer, (h_in, h_out) in enumerate(zip(dims, dims[1:])):
+            gain = 1.0 if nonlinearity is None or layer == 0 else math.sqrt(2)
+            layers.append(ScalarLinearLayer(h_in, h_out, alpha=gain / math.sqrt(h_in)))
+            if layer != nl - 1 and nonlinearity is not None:
+                layers.append(torch.nn.SiLU())
+        self.mlp = torch.nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.mlp(x)
+
+
+class Linear(torch.nn.Module):
+    """e3nn ``o3.Linear(irreps_in, irreps_out)`` (internal shared weights, no bias,
+    path_normalization="element"): out_b = (1/sqrt(sum_a mul_a)) sum_a x_a W_ab over equal irreps."""
+
+    def __init__(self, irreps_in, irreps_out):
+        super().__init__()
+        self.irreps_in, self.irreps_out = Irreps(irreps_in), Irreps(irreps_out)
+        self.instr: List[Tuple[int, int, int, float]] = []  # (i_in, i_out, weight offset, path weight)
+        off = 0
+        pairs = [
+            (i, o)
+            for i, (_, ir_i) in enumerate(self.irreps_in)
+            for o, (_, ir_o) in enumerate(self.irreps_out)
+            if ir_i == ir_o
+        ]
+        for (i, o) in pairs:
+            fan = sum(self.irreps_in[i2][0] for (i2, o2) in pairs if o2 == o)
+            self.instr.append((i, o, off, 1.0 / math.sqrt(fan)))
+            off += self.irreps_in[i][0] * self.irreps_out[o][0]
+        self.weight_numel = off
+        self.weight = torch.nn.Parameter(torch.randn(off))
+        self._in_sl, self._out_sl = self.irreps_in.slices(), self.irreps_out.slices()
+
+    def forward(self, x):
+        N = x.shape[0]
+        outs: List[Optional[torch.Tensor]] = [None] * len(self.irreps_out)
+        for (i, o, off, pw) in self.instr:
+            mi, ir = self.irreps_in[i]
+            mo = self.irreps_out[o][0]
+            W = self.weight[off: off + mi * mo].view(mi, mo) * pw
+            xi = x[:, self._in_sl[i]].reshape(N, mi, ir.dim)
+            # [N, d, mi] @ [mi, mo] -> [N, d, mo] -> [N, mo, d]
+            r = torch.matmul(xi.transpose(1, 2), W).transpose(1, 2).reshape(N, mo * ir.dim)
+            outs[o] = r if outs[o] is None else outs[o] + r
+        for o, (mo, ir) in enumerate(self.irreps_out):
+            if outs[o] is None:
+                outs[o] = x.new_zeros(N, mo * ir.dim)
+        return torch.cat(outs, dim=1)
+
+
+class SelfConnection(torch.nn.Module):
+    """e3nn ``FullyConnectedTensorProduct(feature_irreps_in, F0 x 0e, feature_irreps_out)``
+    (interaction_block.py:140-146): out_b[w,k] = (1/sqrt(sum_a mul_a F0)) sum_a sum_uv W_ab[u,v,w] x_a[u,k] attr[v]."""
+
+    def __init__(self, irreps_in, num_attr: int, irreps_out):
+        super().__init__()
+        self.irreps_in, self.irreps_out, self.num_attr = Irreps(irreps_in), Irreps(irreps_out), num_attr
+        pairs = [
+            (i, o)
+            for i, (_, ir_i) in enumerate(self.irreps_in)
+            for o, (_, ir_o) in enumerate(self.irreps_out)
+            if ir_i == ir_o
+        ]
+        self.instr: List[Tuple[int, int, int, float]] = []
+        off = 0
+        for (i, o) in pairs:
+            fan = sum(self.irreps_in[i2][0] * num_attr for (i2, o2) in pairs if o2 == o)
+            self.instr.append((i, o, off, 1.0 / math.sqrt(fan)))
+            off += self.irreps_in[i][0] * num_attr * self.irreps_out[o][0]
+        self.weight_numel = off
+        self.weight = torch.nn.Parameter(torch.randn(off))
+        self._in_sl = self.irreps_in.slices()
+
+    def forward(self, x, node_attrs):
+        N = x.shape[0]
+        outs: List[Optional[torch.Tensor]] = [None] * len(self.irreps_out)
+        for (i, o, off, pw) in self.instr:
+            mi, ir = self.irreps_in[i]
+            mo = self.irreps_out[o][0]
+            W = self.weight[off: off + mi * self.num_attr * mo].view(mi, self.num_attr, mo)
+            xi = x[:, self._in_sl[i]].reshape(N, mi, ir.dim)
+            r = pw * torch.einsum("uvw,nuk,nv->nwk", W, xi, node_attrs).reshape(N, mo * ir.dim)
+            outs[o] = r if outs[o] is None else outs[o] + r
+        for o, (mo, ir) in enumerate(self.irreps_out):
+            if outs[o] is None:
+                outs[o] = x.new_zeros(N, mo * ir.dim)
+        return torch.cat(outs, dim=1)
+
+
+class Gate(torch.nn.Module):
+    """e3nn ``nn.Gate`` with normalize2mom'd SiLU (even) / tanh (odd) (convnetlayer.py:42-56,104-112)."""
+
+    def __init__(self, irreps_scalars, irreps_gates, irreps_gated):
+        super().__init__()
+        self.irreps_scalars, self.irreps_gates, self.irreps_gated = (
+            Irreps(irreps_scalars), Irreps(irreps_gates), Irreps(irreps_gated))
+        self.irreps_in = self.irreps_scalars + self.irreps_gates + self.irreps_gated
+        gp = self.irreps_gates[0][1].p if len(self.irreps_gates) else 1
+        self.irreps_out = self.irreps_scalars + Irreps([(m, Irrep(ir.l, ir.p * gp)) for m, ir in self.irreps_gated])
+
+    @staticmethod
+    def _act(x, p: int):
+        return torch.nn.functional.silu(x) * C_SILU if p == 1 else torch.tanh(x) * C_TANH
+
+    def forward(self, x):
+        N = x.shape[0]
+        ns, ng = self.irreps_scalars.dim, self.irreps_gates.dim
+        parts = []
+        off = 0
+        for mul, ir in self.irreps_scalars:
+            parts.append(self._act(x[:, off: off + mul], ir.p))
+            off += mul
+        if len(self.irreps_gated):
+            gates = []
+            goff = ns
+            for mul, ir in self.irreps_gates:
+                gates.append(self._act(x[:, goff: goff + mul], ir.p))
+                goff += mul
+            gates = torch.cat(gates, dim=1)
+            off = ns + ng
+            g0 = 0
+            for mul, ir in self.irreps_gated:
+                ch = x[:, off: off + mul * ir.dim].reshape(N, mul, ir.dim)
+                parts.append((ch * gates[:, g0: g0 + mul].unsqueeze(-1)).reshape(N, mul * ir.dim))
+                off += mul * ir.dim
+                g0 += mul
+        return torch.cat(parts, dim=1)
+
+
+# ---------------------------------------------------------------------------------------
+# graph modules
+# ---------------------------------------------------------------------------------------
+class InteractionBlock(torch.nn.Module):
+    """interaction_block.py:21-207 (no ghost exchange here; see nequip_b200.parallel for the sharded path)."""
+
+    def __init__(self, feature_irreps_in, irreps_edge_attr, feature_irreps_out, num_edge_embed: int,
+                 num_node_attrs: int, radial_mlp_depth: int, radial_mlp_width: int, use_sc: bool,
+                 avg_num_neighbors: float):
+        super().__init__()
+        fin, fe, fout = Irreps(feature_irreps_in), Irreps(irreps_edge_attr), Irreps(feature_irreps_out)
+        self.feature_irreps_in, self.irreps_edge_attr, self.feature_irreps_out = fin, fe, fout
+        self.register_buffer("norm_const", torch.tensor(1.0 / math.sqrt(avg_num_neighbors)), persistent=False)
+        self.linear_1 = Linear(fin, fin)
+        irreps_mid, instructions = build_tp_instructions(fin, fe, fout)
+        self.irreps_mid, self.instructions = irreps_mid, instructions
+        self.tp_scatter = B200TensorProductScatter(fin, fe, irreps_mid, instructions)
+        self.edge_mlp = ScalarMLPFunction(num_edge_embed, self.tp_scatter.weight_numel,
+                                          hidden_layers_depth=radial_mlp_depth,
+                                          hidden_layers_width=radial_mlp_width, nonlinearity="silu")
+        self.linear_2 = Linear(irreps_mid.simplify(), fout)
+        self.sc = SelfConnection(fin, num_node_attrs, fout) if use_sc else None
+
+    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index):
+        sc = self.sc(x, node_attrs) if self.sc is not None else None
+        x = self.linear_1(x)
+        x = x * self.norm_const
+        w = self.edge_mlp(edge_embedding)
+        x = self.tp_scatter(x=x, edge_attr=edge_attrs, edge_weight=w, edge_dst=edge_index[0], edge_src=edge_index[1])
+        x = self.linear_2(x)
+        if sc is not None:
+            x = x + sc
+        return x
+
+
+class ConvNetLayer(torch.nn.Module):
+    """convnetlayer.py:26-170 (gate nonlinearity, no resnet)."""
+
+    def __init__(self, prev: Irreps, edge_attr: Irreps, hidden: Irreps, **conv_kwargs):
+        super().__init__()
+        scalars, gates, gated, conv_out, layer_out = gate_irreps(prev, edge_attr, hidden)
+        self.equivariant_nonlin = Gate(scalars, gates, gated)
+        self.conv = InteractionBlock(prev, edge_attr, conv_out, **conv_kwargs)
+        self.irreps_out = layer_out
+
+    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index):
+        x = self.conv(x, node_attrs, edge_attrs, edge_embedding, edge_index)
+        return self.equivariant_nonlin(x)
+
+
+class NequIPEnergyModel(torch.nn.Module):
+    """``NequIPGNNModel`` (nequip_models.py:116-210) wrapped in the force part of
+    ``ForceStressOutput`` (grad_output.py:215-232).  ``forward(data) -> data`` on an
+    AtomicDataDict-shaped dict: needs ``pos`` [N,3] f64, ``edge_index`` [2,E] i64,
+    ``atom_types`` [N] i64 and, for periodic systems, ``cell`` [3,3] + ``edge_cell_shift`` [E,3]."""
+
+    def __init__(self, *, r_max: float, type_names: Sequence[str], num_layers: int = 4, l_max: int = 1,
+                 parity: bool = True, num_features: int = 32, radial_mlp_depth: int = 1,
+                 radial_mlp_width: int = 128, num_bessels: int = 8, polynomial_cutoff_p: float = 6.0,
+                 avg_num_neighbors: float = 1.0, per_type_energy_scales: Optional[Sequence[float]] = None,
+                 per_type_energy_shifts: Optional[Sequence[float]] = None, model_dtype=torch.float32,
+                 seed: int = 123):
+        super().__init__()
+        self.r_max, self.l_max, self.num_bessels, self.poly_p = float(r_max), l_max, num_bessels, float(polynomial_cutoff_p)
+        self.model_dtype = model_dtype
+        self.config = dict(r_max=r_max, type_names=list(type_names), num_layers=num_layers, l_max=l_max, parity=parity,
+                           num_features=num_features, radial_mlp_depth=radial_mlp_depth,
+                           radial_mlp_width=radial_mlp_width, num_bessels=num_bessels,
+                           polynomial_cutoff_p=polynomial_cutoff_p, avg_num_neighbors=avg_num_neighbors)
+        prev_default = torch.get_default_dtype()
+        torch.set_default_dtype(model_dtype)
+        try:
+            torch.manual_seed(seed)  # model_builder seeds before construction (model/utils.py:104-230)
+            ntypes = len(type_names)
+            self.type_embed = torch.nn.Embedding(ntypes, num_features)
+            edge_attr = Irreps.spherical_harmonics(l_max)
+            prev = Irreps([(num_features, Irrep(0, 1))])
+            hid = hidden_irreps(l_max, num_features, parity)
+            hiddens = [hid] * (num_layers - 1) + [Irreps([(num_features, Irrep(0, 1))])]
+            layers = []
+            for li, h in enumerate(hiddens):
+                layer = ConvNetLayer(prev, edge_attr, h, num_edge_embed=num_bessels, num_node_attrs=num_features,
+                                     radial_mlp_depth=radial_mlp_depth, radial_mlp_width=radial_mlp_width,
+                                     use_sc=(li != 0), avg_num_neighbors=avg_num_neighbors)
+                layers.append(layer)
+                prev = layer.irreps_out
+            self.layers = torch.nn.ModuleList(layers)
+            self.readout = ScalarMLPFunction(prev.dim, 1, hidden_layers_depth=0)
+        finally:
+            torch.set_default_dtype(prev_default)
+        sc = None if per_type_energy_scales is None else torch.as_tensor(per_type_energy_scales, dtype=torch.float64).reshape(-1, 1)
+        sh = None if per_type_energy_shifts is None else torch.as_tensor(per_type_energy_shifts, dtype=torch.float64).reshape(-1, 1)
+        self.register_buffer("scales", sc if sc is not None else torch.empty(0, dtype=torch.float64))
+        self.register_buffer("shifts", sh if sh is not None else torch.empty(0, dtype=torch.float64))
+
+    # the energy part (SequentialGraphNetwork order of nequip_models.py:288-399)
+    def energy(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        pos = data[POSITIONS_KEY]
+        edge_index = data[EDGE_INDEX_KEY]
+        types = data[ATOM_TYPE_KEY].view(-1)
+        node_attrs = self.type_embed(types)
+        x = node_attrs
+        shift, cell = data.get(EDGE_CELL_SHIFT_KEY), data.get(CELL_KEY)
+        if cell is None:
+            shift = None
+        _vec, edge_attrs, edge_embedding = ops.edge_embed(
+            pos, edge_index, shift, cell, lmax=self.l_max, num_bessel=self.num_bessels, r_max=self.r_max,
+            poly_p=self.poly_p, prefactor=(2 * math.pi) / (self.r_max * self.r_max), out_dtype=self.model_dtype)
+        for layer in self.layers:
+            x = layer(x, node_attrs, edge_attrs, edge_embedding, edge_index)
+        e_atom = self.readout(x).to(torch.float64)
+        if self.scales.numel():
+            e_atom = e_atom * self.scales[types]
+        if self.shifts.numel():
+            e_atom = e_atom + self.shifts[types]
+        data[PER_ATOM_ENERGY_KEY] = e_atom
+        data[TOTAL_ENERGY_KEY] = e_atom.sum(dim=0, keepdim=True)
+        return data
+
+    def forward(self, data: Dict[str, torch.Tensor], compute_forces: bool = True) -> Dict[str, torch.Tensor]:
+        data = dict(data)
+        if not compute_forces:
+            return self.energy(data)
+        pos = data[POSITIONS_KEY]
+        with torch.enable_grad():
+            pos = pos.detach().requires_grad_(True)
+            data[POSITIONS_KEY] = pos
+            data = self.energy(data)
+            (g,) = torch.autograd.grad([data[TOTAL_ENERGY_KEY].sum()], [pos])
+        data[FORCE_KEY] = torch.neg(g)
+        data[POSITIONS_KEY] = pos.detach()
+        data[TOTAL_ENERGY_KEY] = data[TOTAL_ENERGY_KEY].detach()
+        data[PER_ATOM_ENERGY_KEY] = data[PER_ATOM_ENERGY_KEY].detach()
+        return data

@@ -1,0 +1,324 @@
+"""Torch-facing operators over the C ABI (device memory, streams and autograd glue only).
+
+``tp_scatter``  -- the fused tensor product + scatter that replaces
+                   ``TensorProductScatter.forward`` (nequip/nn/_tp_scatter_base.py:35-38)
+                   and its autograd (first order: what forces need,
+                   nequip/nn/grad_output.py:217-221 with ``create_graph=False``).
+``spherical_harmonics`` / ``edge_embed`` -- the edge-embedding kernels replacing
+                   nequip/nn/embedding/_edge.py:65-80,136-150,193-198 + nequip/nn/utils.py:68-118.
+
+There is no CPU or eager fallback: CPU tensors raise, a missing/unbuildable kernel
+library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _capi, build
+from .codegen import GenOptions, TPSignature
+from .irreps import Irreps
+
+_DT = {torch.float32: 0, torch.float64: 1}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts: torch.Tensor):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "nequip_b200 kernels run on CUDA (sm_100a) only; got a CPU tensor and there is no CPU fallback"
+            )
+
+
+# ---------------------------------------------------------------------------------------
+# plans
+# ---------------------------------------------------------------------------------------
+class TPPlan:
+    """Immutable binding of one TensorProductScatter signature to its kernel library."""
+
+    def __init__(self, irreps_in1, irreps_in2, irreps_out, instructions, opts: Optional[GenOptions] = None):
+        self.sig = TPSignature(Irreps(irreps_in1), Irreps(irreps_in2), Irreps(irreps_out), list(instructions))
+        self.opts = opts or GenOptions()
+        self.spec_path = build.ensure_spec(self.sig, self.opts)
+        L = _capi.lib()
+
+        def arr(irr):
+            a = (_capi.NqbIrrep * len(irr))()
+            for i, (mul, ir) in enumerate(irr):
+                a[i].mul, a[i].l, a[i].p = mul, ir.l, ir.p
+            return a
+
+        in1, in2, out = arr(self.sig.irreps_in1), arr(self.sig.irreps_in2), arr(self.sig.irreps_out)
+        ins = (_capi.NqbInstruction * len(self.sig.instructions))()
+        for i, (a, b, c) in enumerate(self.sig.instructions):
+            ins[i].i_in1, ins[i].i_in2, ins[i].i_out = a, b, c
+        h = C.c_void_p()
+        _capi.check(
+            L.nqb_plan_create(in1, len(in1), in2, len(in2), out, len(out), ins, len(ins),
+                              self.spec_path.encode(), C.byref(h)),
+            "nqb_plan_create",
+        )
+        self._h = h
+        self.d_in, self.s_dim = self.sig.d_in, self.sig.s_dim
+        self.weight_numel, self.d_out = self.sig.weight_numel, self.sig.d_out
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _capi.lib().nqb_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+_plans: Dict[str, TPPlan] = {}
+_plans_lock = threading.Lock()
+
+
+def get_plan(irreps_in1, irreps_in2, irreps_out, instructions, opts: Optional[GenOptions] = None) -> TPPlan:
+    opts = opts or GenOptions()
+    sig = TPSignature(Irreps(irreps_in1), Irreps(irreps_in2), Irreps(irreps_out), list(instructions))
+    key = sig.canonical() + "|" + opts.tag()
+    with _plans_lock:
+        p = _plans.get(key)
+        if p is None:
+            p = TPPlan(irreps_in1, irreps_in2, irreps_out, instructions, opts)
+            _plans[key] = p
+        return p
+
+
+# ---------------------------------------------------------------------------------------
+# destination CSR
+# ---------------------------------------------------------------------------------------
+@dataclass
+class EdgeCSR:
+    row_ptr: torch.Tensor  # [N+1] int64
+    perm: Optional[torch.Tensor]  # [E] int64 (slot -> edge id) or None when edges are already grouped
+    num_nodes: int
+    num_edges: int
+
+
+def build_csr(edge_dst: torch.Tensor, num_nodes: int, assume_sorted: Optional[bool] = None) -> EdgeCSR:
+    """CSR over edges grouped by destination.  ``assume_sorted=None`` checks on the
+    device (one host sync); the reference's neighbour lists are grouped by centre atom
+    (nequip/data/transforms/neighborlist.py:120-157) so the common case needs no sort."""
+    _require_cuda(edge_dst)
+    if edge_dst.dtype != torch.int64:
+        edge_dst = edge_dst.long()
+    edge_dst = edge_dst.contiguous()
+    E = edge_dst.numel()
+    L = _capi.lib()
+    st = _stream()
+    is_sorted = assume_sorted
+    if is_sorted is None:
+        flag = torch.empty(1, dtype=torch.int32, device=edge_dst.device)
+        _capi.check(L.nqb_csr_check_sorted(_ptr(edge_dst), E, _ptr(flag), st), "nqb_csr_check_sorted")
+        is_sorted = bool(flag.item())
+    perm = None
+    keys = edge_dst
+    if not is_sorted:
+        keys, perm = torch.sort(edge_dst, stable=True)
+        perm = perm.contiguous()
+        keys = keys.contiguous()
+    row_ptr = torch.empty(num_nodes + 1, dtype=torch.int64, device=edge_dst.device)
+    _capi.check(L.nqb_csr_from_sorted(_ptr(keys), E, num_nodes, _ptr(row_ptr), st), "nqb_csr_from_sorted")
+    return EdgeCSR(row_ptr, perm, num_nodes, E)
+
+
+class _CSRCache:
+    """Per-thread one-entry cache: all layers of one forward share the same edge_index."""
+
+    def __init__(self):
+        self._tls = threading.local()
+
+    def get(self, edge_dst: torch.Tensor, num_nodes: int) -> EdgeCSR:
+        key = (edge_dst.data_ptr(), edge_dst.numel(), edge_dst._version, num_nodes, edge_dst.device)
+        ent = getattr(self._tls, "ent", None)
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        csr = build_csr(edge_dst, num_nodes)
+        # hold a reference to edge_dst so the data_ptr cannot be recycled while cached
+        self._tls.ent = (key, csr, edge_dst)
+        return csr
+
+    def clear(self):
+        self._tls.ent = None
+
+
+csr_cache = _CSRCache()
+
+
+# ---------------------------------------------------------------------------------------
+# fused TP + scatter
+# ---------------------------------------------------------------------------------------
+class _TPScatterFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, edge_attr, edge_weight, edge_src, plan: TPPlan, csr: EdgeCSR):
+        L = _capi.lib()
+        N, E = x.shape[0], edge_src.numel()
+        out = torch.empty((N, plan.d_out), dtype=x.dtype, device=x.device)
+        if N > 0:
+            _capi.check(
+                L.nqb_tp_scatter_fwd(plan.handle, _DT[x.dtype], _ptr(x), _ptr(edge_attr), _ptr(edge_weight),
+                                     _ptr(csr.row_ptr), _ptr(csr.perm), _ptr(edge_src), N, E, _ptr(out), _stream()),
+                "nqb_tp_scatter_fwd",
+            )
+        ctx.plan, ctx.csr = plan, csr
+        ctx.save_for_backward(x, edge_attr, edge_weight, edge_src)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        x, y, w, edge_src = ctx.saved_tensors
+        plan, csr = ctx.plan, ctx.csr
+        L = _capi.lib()
+        N, E = x.shape[0], edge_src.numel()
+        need_x = ctx.needs_input_grad[0]
+        gx = torch.zeros_like(x) if need_x else None
+        gy = torch.zeros_like(y)
+        gw = torch.empty_like(w)
+        if N > 0 and E > 0:
+            gout = gout.contiguous()
+            _capi.check(
+                L.nqb_tp_scatter_bwd(plan.handle, _DT[x.dtype], _ptr(x), _ptr(y), _ptr(w), _ptr(csr.row_ptr),
+                                     _ptr(csr.perm), _ptr(edge_src), _ptr(gout), N, E, _ptr(gx), _ptr(gy), _ptr(gw),
+                                     _stream()),
+                "nqb_tp_scatter_bwd",
+            )
+        elif E == 0:
+            gw.zero_()
+        return gx, (gy if ctx.needs_input_grad[1] else None), (gw if ctx.needs_input_grad[2] else None), None, None, None
+
+
+def tp_scatter(plan: TPPlan, x, edge_attr, edge_weight, edge_dst, edge_src, csr: Optional[EdgeCSR] = None):
+    """``out[n] = sum_{e: dst[e]=n} TP_uvu(x[src[e]], edge_attr[e], edge_weight[e])`` -> ``[x.size(0), D_mid]``."""
+    _require_cuda(x, edge_attr, edge_weight, edge_dst, edge_src)
+    if x.dtype not in _DT:
+        raise TypeError(f"nequip_b200.tp_scatter: unsupported dtype {x.dtype}")
+    dt = x.dtype
+    if x.dim() != 2 or x.shape[1] != plan.d_in:
+        raise ValueError(f"x must be [N, {plan.d_in}], got {tuple(x.shape)}")
+    E = edge_src.numel()
+    if tuple(edge_attr.shape) != (E, plan.s_dim) or tuple(edge_weight.shape) != (E, plan.weight_numel):
+        raise ValueError(
+            f"edge_attr/edge_weight must be [{E}, {plan.s_dim}] / [{E}, {plan.weight_numel}], got "
+            f"{tuple(edge_attr.shape)} / {tuple(edge_weight.shape)}"
+        )
+    if edge_dst.numel() != E:
+        raise ValueError("edge_dst and edge_src differ in length")
+    x = x.contiguous()
+    y = edge_attr.to(dt).contiguous()
+    w = edge_weight.to(dt).contiguous()
+    src = edge_src.long().contiguous()
+    if csr is None:
+        csr = csr_cache.get(edge_dst.long().contiguous() if edge_dst.dtype != torch.int64 else edge_dst, x.shape[0])
+    elif csr.num_nodes != x.shape[0] or csr.num_edges != E:
+        raise ValueError("EdgeCSR does not match x / edge_index")
+    return _TPScatterFn.apply(x, y, w, src, plan, csr)
+
+
+# ---------------------------------------------------------------------------------------
+# spherical harmonics / edge embedding
+# ---------------------------------------------------------------------------------------
+class _SHFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec, lmax: int, out_dtype):
+        L = _capi.lib()
+        E = vec.shape[0]
+        y = torch.empty((E, (lmax + 1) ** 2), dtype=out_dtype, device=vec.device)
+        _capi.check(L.nqb_sh_fwd(lmax, _ptr(vec), E, _DT[out_dtype], _ptr(y), _stream()), "nqb_sh_fwd")
+        ctx.lmax, ctx.out_dtype = lmax, out_dtype
+        ctx.save_for_backward(vec)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        (vec,) = ctx.saved_tensors
+        L = _capi.lib()
+        E = vec.shape[0]
+        gvec = torch.empty_like(vec)
+        gy = gy.to(ctx.out_dtype).contiguous()
+        _capi.check(L.nqb_sh_bwd(ctx.lmax, _ptr(vec), E, _DT[ctx.out_dtype], _ptr(gy), _ptr(gvec), _stream()),
+                    "nqb_sh_bwd")
+        return gvec, None, None
+
+
+def spherical_harmonics(vec: torch.Tensor, lmax: int, out_dtype=torch.float32) -> torch.Tensor:
+    """``o3.SphericalHarmonics(lmax, normalize=True, "component")`` of ``[E,3]`` float64 edge vectors."""
+    _require_cuda(vec)
+    if vec.dim() != 2 or vec.shape[1] != 3:
+        raise ValueError("vec must be [E, 3]")
+    return _SHFn.apply(vec.double().contiguous(), int(lmax), out_dtype)
+
+
+class _EdgeEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, edge_index, shift, cell, lmax, num_bessel, r_max, poly_p, prefactor, out_dtype):
+        L = _capi.lib()
+        N, E = pos.shape[0], edge_index.shape[1]
+        dev = pos.device
+        vec = torch.empty((E, 3), dtype=torch.float64, device=dev)
+        y = torch.empty((E, (lmax + 1) ** 2), dtype=out_dtype, device=dev)
+        emb = torch.empty((E, num_bessel), dtype=out_dtype, device=dev)
+        _capi.check(
+            L.nqb_edge_embed_fwd(lmax, num_bessel, r_max, poly_p, prefactor, _ptr(pos), _ptr(edge_index), _ptr(shift),
+                                 _ptr(cell), N, E, _DT[out_dtype], _ptr(vec), _ptr(y), _ptr(emb), _stream()),
+            "nqb_edge_embed_fwd",
+        )
+        ctx.args = (lmax, num_bessel, r_max, poly_p, prefactor, out_dtype, N)
+        ctx.save_for_backward(vec, edge_index)
+        ctx.mark_non_differentiable(vec)
+        return vec, y, emb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _gvec, gy, gemb):
+        vec, edge_index = ctx.saved_tensors
+        lmax, num_bessel, r_max, poly_p, prefactor, out_dtype, N = ctx.args
+        L = _capi.lib()
+        E = vec.shape[0]
+        gpos = torch.zeros((N, 3), dtype=torch.float64, device=vec.device)
+        gy = None if gy is None else gy.to(out_dtype).contiguous()
+        gemb = None if gemb is None else gemb.to(out_dtype).contiguous()
+        _capi.check(
+            L.nqb_edge_embed_bwd(lmax, num_bessel, r_max, poly_p, prefactor, _ptr(vec), _ptr(edge_index), N, E,
+                                 _DT[out_dtype], _ptr(gy), _ptr(gemb), _ptr(gpos), 0, _stream()),
+            "nqb_edge_embed_bwd",
+        )
+        return gpos, None, None, None, None, None, None, None, None, None
+
+
+def edge_embed(pos, edge_index, shift=None, cell=None, *, lmax: int, num_bessel: int = 8, r_max: float,
+               poly_p: float = 6.0, prefactor: float = 1.0, out_dtype=torch.float32):
+    """Edge vectors, harmonics and Bessel x cutoff embedding in one kernel.
+
+    Returns ``(edge_vectors [E,3] f64, edge_attrs [E,(lmax+1)^2], edge_embedding [E,num_bessel])``.
+    Differentiable w.r.t. ``pos`` (forces); the cell gradient (stress) is not provided here."""
+    _require_cuda(pos, edge_index)
+    pos = pos.double().contiguous()
+    edge_index = edge_index.long().contiguous()
+    if (shift is None) != (cell is None):
+        raise ValueError("shift and cell must be given together")
+    if shift is not None:
+        shift = shift.double().contiguous()
+        cell = cell.double().reshape(3, 3).contiguous()
+    return _EdgeEmbedFn.apply(pos, edge_index, shift, cell, int(lmax), int(num_bessel), float(r_max),
+                              float(poly_p), float(prefactor), out_dtype)
