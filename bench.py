@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s (energy + forces) of the NequIP hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (own arm: sm_100a kernels)
+  python bench.py --impl reference --gpus N --steps K ...  (reference arm: the e3nn-formulation
+                                                            CPU path = oracle port, all host threads,
+                                                            bounded sample of the same workload)
+
+A "step" is one energy+forces evaluation (forward + autograd backward w.r.t. positions) of the
+BASELINE.json configs[2] model -- NequIP l_max=2, 4 layers, 64 features, parity, radial MLP 1x128,
+r_max 5 A -- on a synthetic ~10k-atom Li3PO4-like periodic box (10 648 atoms, ~589k edges).
+`value`  : device-resident inputs, CUDA-event timed, max over ranks.
+`e2e`    : the same step through NequIPEnergyModel.forward with HOST (pinned) inputs: H2D of
+           pos/edge_index/shifts/types/cell and D2H of forces+energy inside the timed region.
+`roofline`: the fused TP+scatter forward kernel of the largest layer, timed alone with CUDA
+           events on the launching stream, algorithmic bytes / duration vs the measured HBM peak.
+N > 1: one process per GPU (torchrun), each rank owns an independent frame of the same size
+(data-parallel over frames, as the reference's DDP does; "weak"), one NCCL all-reduce of the
+per-frame energies per step.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (structure kind, n_side, model kwargs)
+    "li3po4_10k_l2_f64": ("li3po4", 22, dict(l_max=2, num_layers=4, num_features=64, radial_mlp_depth=1, radial_mlp_width=128)),
+    "water_1k_l2_f32": ("water", 10, dict(l_max=2, num_layers=4, num_features=32, radial_mlp_depth=1, radial_mlp_width=128)),
+    "asi_50k_l3_f32": ("asi", 37, dict(l_max=3, num_layers=5, num_features=32, radial_mlp_depth=1, radial_mlp_width=128)),
+    "tiny": ("water", 5, dict(l_max=2, num_layers=3, num_features=8, radial_mlp_depth=1, radial_mlp_width=16)),
+}
+CPU_SAMPLE_NSIDE = {"li3po4_10k_l2_f64": 9, "water_1k_l2_f32": 8, "asi_50k_l3_f32": 9, "tiny": 4}
+R_MAX = 5.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def tp_algorithmic_bytes(sig, N, E, elem=4, backward=False):
+    """forward reads x, edge_attr, edge_weight, two int64 index arrays, writes out."""
+    b = elem * (N * sig.d_in + E * sig.s_dim + E * sig.weight_numel + N * sig.d_out) + 16 * E
+    if backward:
+        b = elem * (N * sig.d_out + N * sig.d_in + E * sig.s_dim + 2 * E * sig.weight_numel + E * sig.s_dim
+                    + N * sig.d_in) + 16 * E
+    return b
+
+
+def build_system(workload, seed, n_side=None):
+    from nequip_b200 import data as D
+
+    kind, ns, mk = WORKLOADS[workload]
+    sysd = D.make_system(kind, n_side or ns, r_max=R_MAX, seed=seed)
+    meta = sysd.pop("_meta")
+    return sysd, meta, mk
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own (e3nn-formulation) CPU implementation of the path -- the
+    oracle port -- with all host threads, on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from nequip_b200.nn.model import NequIPEnergyModel
+    from oracle import model as omodel
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ns = CPU_SAMPLE_NSIDE[args.workload]
+    sysd, meta, mk = build_system(args.workload, seed=0, n_side=ns)
+    model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
+                              avg_num_neighbors=meta["avg_num_neighbors"], **mk)
+    sd, cfg = model.state_dict(), model.config
+    n_atoms = sysd["pos"].shape[0]
+    chunk = 20000
+    for _ in range(args.warmup):
+        omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=chunk)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=chunk)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_atoms / dt
+    sample = f"{n_atoms}-atom {WORKLOADS[args.workload][0]} box, same model/density, E={sysd['edge_index'].shape[1]}, edge chunk {chunk}"
+    line = {
+        "impl": "reference", "metric": "atom-steps/sec (energy+forces)", "value": val, "unit": "atom-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": "CPU e3nn-formulation path (oracle port), bounded sample"},
+        "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(workload):
+    from nequip_b200.nn.model import NequIPEnergyModel
+    from oracle import model as omodel
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ns = CPU_SAMPLE_NSIDE[workload]
+    sysd, meta, mk = build_system(workload, seed=0, n_side=ns)
+    model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
+                              avg_num_neighbors=meta["avg_num_neighbors"], **mk)
+    sd, cfg = model.state_dict(), model.config
+    n_atoms = sysd["pos"].shape[0]
+    omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=20000)
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 20):
+        omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=20000)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n_atoms / dt, "unit": "atom-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n_atoms}-atom {WORKLOADS[workload][0]} box (same model, density, r_max), {reps} steps, E={sysd['edge_index'].shape[1]}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="li3po4_10k_l2_f64", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run one warm-up step, then ONE step between cudaProfilerStart/Stop (for ncu "
+                         "--profile-from-start off); prints no bench line")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    from nequip_b200 import _capi, ops
+    from nequip_b200 import data as D
+    from nequip_b200.nn.model import NequIPEnergyModel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    # every rank owns its own frame (same size/density, different seed)
+    sysd, meta, mk = build_system(args.workload, seed=rank)
+    n_atoms, n_edges = sysd["pos"].shape[0], sysd["edge_index"].shape[1]
+    model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
+                              avg_num_neighbors=meta["avg_num_neighbors"], **mk).to(dev)
+    for p in model.parameters():
+        p.requires_grad_(False)  # inference: forces only need d/dpos
+
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in sysd.items()}
+    resident = D.to_device(sysd, dev)
+    e_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step_resident():
+        out = model(resident)
+        if world > 1:
+            e_buf.copy_(out["total_energy"].view(-1))
+            dist.all_reduce(e_buf)
+        return out
+
+    f_host = torch.empty((n_atoms, 3), dtype=torch.float64).pin_memory()
+    e_host = torch.empty((1,), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+        out = model(d)
+        if world > 1:
+            e_buf.copy_(out["total_energy"].view(-1))
+            dist.all_reduce(e_buf)
+        f_host.copy_(out["forces"], non_blocking=True)
+        e_host.copy_(out["total_energy"].view(-1), non_blocking=True)
+        return out
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _capi.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1) / steps
+        launches = _capi.launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    if args.profile_step:
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    d2h = f_host.numel() * 8 + 8
+
+    # ---- roofline of the dominant kernel: fused TP+scatter forward of the largest layer, alone
+    roof = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        layer = max(model.layers, key=lambda l: l.conv.tp_scatter.weight_numel)
+        tps = layer.conv.tp_scatter
+        sig = tps._plan.sig
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randn(n_atoms, sig.d_in, device=dev, generator=g)
+        y = torch.randn(n_edges, sig.s_dim, device=dev, generator=g)
+        w = torch.randn(n_edges, sig.weight_numel, device=dev, generator=g)
+        ei = resident["edge_index"]
+        csr = ops.build_csr(ei[0].contiguous(), n_atoms)
+        src = ei[1].contiguous()
+        with torch.no_grad():
+            for _ in range(3):
+                ops.tp_scatter(tps._plan, x, y, w, ei[0], src, csr=csr)
+            torch.cuda.synchronize()
+            reps = max(5, args.steps)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                ops.tp_scatter(tps._plan, x, y, w, ei[0], src, csr=csr)
+            e1.record()
+            torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        alg = tp_algorithmic_bytes(sig, n_atoms, n_edges)
+        ach = alg / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "tp_fwd_kernel<float> (fused TP+scatter forward)", "layer_signature_W": sig.weight_numel,
+                "alg_bytes_per_launch": alg, "ms_per_launch": k_ms, "peak_source": peak_src,
+                "inputs": "w stream %.2f GB >> 126 MB L2" % (n_edges * sig.weight_numel * 4 / 1e9)}
+        # backward kernel too (reported, not the headline roofline)
+        xg = x.clone().requires_grad_(True)
+        yg = y.clone().requires_grad_(True)
+        wg = w.clone().requires_grad_(True)
+        out = ops.tp_scatter(tps._plan, xg, yg, wg, ei[0], src, csr=csr)
+        go = torch.randn_like(out)
+        for _ in range(2):
+            torch.autograd.grad(out, [xg, yg, wg], go, retain_graph=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            torch.autograd.grad(out, [xg, yg, wg], go, retain_graph=True)
+        e1.record()
+        torch.cuda.synchronize()
+        b_ms = e0.elapsed_time(e1) / reps
+        algb = tp_algorithmic_bytes(sig, n_atoms, n_edges, backward=True)
+        roof["backward"] = {"ms_per_launch": b_ms, "alg_bytes_per_launch": algb,
+                            "achieved": algb / (b_ms * 1e-3) / 1e9, "frac": algb / (b_ms * 1e-3) / 1e9 / peak,
+                            "note": "includes torch.zeros_like for grad_x/grad_y"}
+        del x, y, w, xg, yg, wg, out, go
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.workload)
+
+    if rank == 0:
+        total_atoms = n_atoms * world
+        line = {
+            "metric": "atom-steps/sec (energy+forces)",
+            "value": total_atoms / (ms_res * 1e-3),
+            "unit": "atom-steps/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_res,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": args.workload,
+                "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges, "r_max": R_MAX, "parity": True, **mk,
+                "parallelism": f"dp{world} over frames (one {n_atoms}-atom frame per GPU)",
+                "l2_policy": "inputs larger than L2 (edge weights of one layer: %.2f GB)" % (
+                    n_edges * max(l.conv.tp_scatter.weight_numel for l in model.layers) * 4 / 1e9),
+            },
+            "e2e": {"value": total_atoms / (ms_e2e * 1e-3), "unit": "atom-steps/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

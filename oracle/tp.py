@@ -76,7 +76,14 @@ def tensor_product_uvu(
         b = x2[:, s2[i2]].reshape(E, m2, 2 * l2 + 1)
         w = weight[:, woff : woff + m1 * m2].reshape(E, m1, m2)
         woff += m1 * m2
-        r = c * torch.einsum("ijk,zuv,zui,zvj->zuk", C, w, a, b)
+        if m2 == 1:
+            # e3nn's generated code for 'uvu': outer product xx = x1 (x) x2, contract with the
+            # w3j as one dense matmul, then scale by the per-edge weight
+            xx = (a.unsqueeze(-1) * b.reshape(E, 1, 1, 2 * l2 + 1)).reshape(E * m1, (2 * l1 + 1) * (2 * l2 + 1))
+            r = torch.mm(xx, C.reshape((2 * l1 + 1) * (2 * l2 + 1), 2 * l3 + 1)).reshape(E, m1, 2 * l3 + 1)
+            r = c * r * w.reshape(E, m1, 1)
+        else:
+            r = c * torch.einsum("ijk,zuv,zui,zvj->zuk", C, w, a, b)
         r = r.reshape(E, m1 * (2 * l3 + 1))
         out_chunks[io] = r if out_chunks[io] is None else out_chunks[io] + r
     assert woff == weight.shape[1]

@@ -1,0 +1,143 @@
+"""CPU: host-side logic of the product (irreps, CG tables, path tables, generator, neighbour
+lists) and the C-ABI surface (library loads, exports every symbol include/nqb.h declares)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from nequip_b200 import _capi, build, cg
+from nequip_b200 import data as D
+from nequip_b200 import known_signatures as ks
+from nequip_b200.codegen import GenOptions, TPSignature, generate
+from nequip_b200.irreps import Irrep, Irreps, build_tp_instructions
+from oracle import irreps as OI
+from oracle import wigner
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_irreps_parse_sort_simplify():
+    ir = Irreps("32x0e + 32x1o+1e + 2x2e")
+    assert ir.dim == 32 + 96 + 3 + 10 and len(ir) == 4 and ir.num_irreps == 67
+    assert repr(ir) == "32x0e+32x1o+1x1e+2x2e"
+    s, p, inv = Irreps("2x1e+3x0e+1x1o+4x0e").sort()
+    assert repr(s) == "3x0e+4x0e+1x1o+2x1e"  # (l,p) order: 1o=(1,-1) before 1e=(1,+1); stable
+    assert p == (3, 0, 2, 1) and inv == (1, 3, 2, 0)
+    assert repr(s.simplify()) == "7x0e+1x1o+2x1e"
+    assert repr(Irreps.spherical_harmonics(3)) == "1x0e+1x1o+1x2e+1x3o"
+    assert [repr(x) for x in Irrep(1, -1) * Irrep(2, 1)] == ["1o", "2o", "3o"]
+    # the product and oracle bookkeeping agree
+    assert OI.fmt(OI.sort(OI.parse("2x1e+3x0e+1x1o+4x0e"))[0]) == repr(s)
+
+
+@pytest.mark.parametrize("cfg,expect", [
+    ((2, 64, 4), [(64, 3, 192, 576), (576, 15, 960, 3264), (1088, 27, 1728, 5952), (1152, 3, 192, 192)]),
+    ((2, 32, 4), [(32, 3, 96, 288), (288, 15, 480, 1632), (544, 27, 864, 2976), (576, 3, 96, 96)]),
+    ((3, 32, 5), [(32, 4, 128, 512), (512, 34, 1088, 4992), (992, 64, 2048, 9472), (1024, 68, 2176, 9984), (1024, 4, 128, 128)]),
+    ((1, 32, 4), [(32, 2, 64, 128), (128, 5, 160, 352), (224, 8, 256, 576), (256, 2, 64, 64)]),
+])
+def test_layer_shapes_match_survey_appendix_B(cfg, expect):
+    got = [(s.d_in, len(s.paths), s.weight_numel, s.d_out) for s in ks.nequip_layer_signatures(*cfg)]
+    assert got == expect
+
+
+def test_instruction_builder_matches_oracle_bookkeeping():
+    fin, fout = "8x0e+8x1e+8x1o+8x2e+8x2o", "8x0e+8x0o+8x1e+8x1o+8x2e+8x2o"
+    mid, ins = build_tp_instructions(fin, Irreps.spherical_harmonics(2), fout)
+    omid, oins = OI.build_tp_instructions(fin, OI.spherical_harmonics(2), fout)
+    assert repr(mid) == OI.fmt(omid)
+    assert [tuple(i[:3]) for i in ins] == [tuple(i[:3]) for i in oins]
+
+
+def test_cg_tables_match_oracle():
+    for l1 in range(4):
+        for l2 in range(4):
+            for l3 in range(abs(l1 - l2), min(3, l1 + l2) + 1):
+                np.testing.assert_allclose(np.array(cg.real_w3j(l1, l2, l3)), wigner.wigner_3j(l1, l2, l3), atol=1e-15)
+    assert len(cg.sparse_w3j(2, 2, 2)) == 25 and len(cg.sparse_w3j(3, 3, 3)) == 42
+
+
+def test_signature_validation():
+    with pytest.raises(NotImplementedError):
+        TPSignature(Irreps("2x0e"), Irreps("2x0e"), Irreps("2x0e"), [(0, 0, 0)])  # edge attr mul > 1
+    with pytest.raises(ValueError):
+        TPSignature(Irreps("2x0e"), Irreps("1x1o"), Irreps("2x0e"), [(0, 0, 0)])  # 0e x 1o !-> 0e
+    with pytest.raises(NotImplementedError):
+        TPSignature(Irreps("2x0e"), Irreps("1x0e"), Irreps("2x0e"), [(0, 0, 0, "uvw", True)])
+    s = ks.nequip_layer_signatures(2, 64, 4)[2]
+    assert s.fma_count() == 487
+    assert all(abs(p.coef - (2 * p.l3 + 1) ** 0.5) < 1e-15 for p in s.paths)
+
+
+def test_generator_emits_packed_fma_source():
+    sig = ks.nequip_layer_signatures(2, 32, 4)[1]
+    src = generate(sig, GenOptions())
+    assert "tp_fwd_kernel" in src and "tp_bwd_kernel" in src and "vfmai(" in src
+    assert 'extern "C" int nqb_spec_fwd' in src and sig.canonical() in src
+    # every path's weight slice is loaded exactly once in the forward
+    for p in sig.paths:
+        assert len(re.findall(rf"const V w{p.idx} = vloadw", src)) == 2  # once fwd, once bwd
+
+
+def test_capi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "nqb.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(nqb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(build.ensure_runtime())
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libnqb.so does not export {name}"
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    assert _capi.lib().nqb_abi_version() == 1
+
+
+def test_plan_create_validates_signature():
+    """Host-only C-ABI calls: plan creation binds the prebuilt kernel library and rejects a mismatched one."""
+    from nequip_b200 import ops
+
+    sigs = ks.nequip_layer_signatures(1, 8, 2)
+    plan = ops.TPPlan(sigs[0].irreps_in1, sigs[0].irreps_in2, sigs[0].irreps_out, sigs[0].instructions)
+    assert (plan.d_in, plan.s_dim, plan.weight_numel, plan.d_out) == (sigs[0].d_in, 4, sigs[0].weight_numel, sigs[0].d_out)
+    L = _capi.lib()
+    buf = ctypes.create_string_buffer(4096)
+    L.nqb_plan_signature(plan.handle, buf, 4096)
+    assert buf.value.decode() == sigs[0].canonical()
+    # wrong library for this signature
+    wrong = build.ensure_spec(sigs[1])
+    in1 = (_capi.NqbIrrep * 1)(_capi.NqbIrrep(8, 0, 1))
+    in2 = (_capi.NqbIrrep * 1)(_capi.NqbIrrep(1, 0, 1))
+    ins = (_capi.NqbInstruction * 1)(_capi.NqbInstruction(0, 0, 0))
+    h = ctypes.c_void_p()
+    rc = L.nqb_plan_create(in1, 1, in2, 1, in1, 1, ins, 1, wrong.encode(), ctypes.byref(h))
+    assert rc != 0 and b"different signature" in L.nqb_last_error()
+    # selection-rule violation is caught by the C side too
+    in2b = (_capi.NqbIrrep * 1)(_capi.NqbIrrep(1, 1, -1))
+    rc = L.nqb_plan_create(in1, 1, in2b, 1, in1, 1, ins, 1, wrong.encode(), ctypes.byref(h))
+    assert rc != 0 and b"selection rules" in L.nqb_last_error()
+
+
+def test_ops_reject_cpu_tensors():
+    from nequip_b200 import ops
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.spherical_harmonics(torch.randn(4, 3, dtype=torch.float64), 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.edge_embed(torch.randn(4, 3), torch.zeros(2, 3, dtype=torch.long), lmax=1, r_max=5.0)
+
+
+def test_neighbor_list_cell_list_vs_bruteforce():
+    pos, cell = D.jittered_lattice(8, 0.104, seed=3)
+    ei, sh = D.neighbor_list(pos, cell, 5.0)
+    ei2, sh2 = D._nl_bruteforce(pos, np.diag(cell), 5.0)
+    assert np.array_equal(ei, ei2) and np.array_equal(sh, sh2)
+    v = pos[ei[1]] - pos[ei[0]] + sh @ cell
+    r = np.linalg.norm(v, axis=1)
+    assert r.max() < 5.0 and r.min() > 0.5
+    # full list: every edge has its reverse
+    fwd = set(zip(ei[0].tolist(), ei[1].tolist(), map(tuple, sh.astype(int).tolist())))
+    assert all((j, i, (-a, -b, -c)) in fwd for (i, j, (a, b, c)) in list(fwd)[:2000])
+    # sorted by (centre, neighbour)
+    assert np.all(np.diff(ei[0]) >= 0)
