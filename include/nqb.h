@@ -120,6 +120,22 @@ int nqb_edge_embed_bwd(int lmax, int num_bessel, double r_max, double poly_p, do
                        int out_dtype, const void* grad_y, const void* grad_emb, double* grad_pos,
                        double* grad_vec, nqb_stream_t st);
 
+/* Radial MLP on the tensor cores (tcgen05, 3xTF32 split = fp32-level accuracy):
+ *   edge_weight[E, W] = silu(emb[E, 8] @ W1s[8, 128]) @ (W2[128, W] * alpha2)
+ * replaces ScalarMLPFunction.forward for the depth-1 / width-128 radial network that
+ * InteractionBlock builds (nequip/nn/mlp.py:80-195,262-268; nequip/nn/interaction_block.py:119-127,196).
+ * W1s is the first-layer weight already multiplied by its alpha.  nqb_mlp_prepare lays the
+ * second-layer weight out for the MMA tiles once per model (two buffers of
+ * nqb_mlp_prepared_bytes(W) bytes each).  W must be a multiple of 32. */
+size_t nqb_mlp_prepared_bytes(int W);
+int nqb_mlp_prepare(const float* W2, float alpha2, int hidden, int W, float* prep_fwd, float* prep_bwd,
+                    nqb_stream_t st);
+int nqb_mlp_fwd(const float* emb, const float* W1s, const float* prep_fwd, int64_t E, int num_bessel,
+                int hidden, int W, float* edge_weight, nqb_stream_t st);
+/* grad_emb[E, 8] = ((grad_w @ (W2 alpha2)^T) * silu'(emb @ W1s)) @ W1s^T   (overwritten) */
+int nqb_mlp_bwd(const float* emb, const float* W1s, const float* prep_bwd, const float* grad_w, int64_t E,
+                int num_bessel, int hidden, int W, float* grad_emb, nqb_stream_t st);
+
 /* number of kernels the library has launched in this process (bench accounting) */
 int64_t nqb_launch_count(void);
 

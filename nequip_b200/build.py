@@ -61,12 +61,13 @@ def runtime_lib_path() -> str:
 def ensure_runtime(force: bool = False) -> str:
     """Build (if stale) and return the path of libnqb.so."""
     out = runtime_lib_path()
-    srcs = [os.path.join(CSRC, "nqb_runtime.cu"), os.path.join(INCLUDE, "nqb.h")]
+    cus = [os.path.join(CSRC, "nqb_runtime.cu"), os.path.join(CSRC, "nqb_mlp.cu")]
+    srcs = cus + [os.path.join(INCLUDE, "nqb.h")]
     with _lock:
         if force or _newer(srcs, out):
             os.makedirs(LIBDIR, exist_ok=True)
             tmp = out + f".tmp{os.getpid()}"
-            _run([nvcc_path(), *ARCH_FLAGS, *COMMON_FLAGS, "-I", INCLUDE, "-o", tmp, srcs[0], "-ldl"])
+            _run([nvcc_path(), *ARCH_FLAGS, *COMMON_FLAGS, "-I", INCLUDE, "-o", tmp, *cus, "-ldl"])
             os.replace(tmp, out)
     return out
 

@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 4
+CODEGEN_VERSION = 6
 
 
 # ---------------------------------------------------------------------------
@@ -166,7 +166,7 @@ class GenOptions:
     nwarp: int = 4  # warps (= destination nodes) per CTA
     acc_cap: int = 32  # max output components per channel held by one warp (forward)
     acc_cap_bwd: int = 24
-    prefetch: bool = False
+    prefetch: bool = True
 
     def tag(self) -> str:
         return f"w{self.nwarp}_a{self.acc_cap}_b{self.acc_cap_bwd}_p{int(self.prefetch)}"
@@ -274,32 +274,82 @@ class TPGenerator:
             b.setdefault((p.i1, p.i2), []).append(p)
         return sorted(b.items())
 
-    def _emit_edge_prologue(self, em: _Emitter, paths: List[Path], want_valid_mask_w: bool):
+    def _edge_vars(self, paths: List[Path]):
+        sig = self.sig
+        yused = sorted({p.yoff + j for p in paths for j in range(2 * p.l2 + 1)})
+        names = [f"y{j}" for j in yused]
+        for i1 in sorted({p.i1 for p in paths}):
+            names += [f"x{i1}_{i}" for i in range(sig.irreps_in1[i1][1].dim)]
+        names += [f"w{p.idx}" for p in paths]
+        return yused, names
+
+    def _emit_edge_decls(self, em: _Emitter, paths: List[Path], sfx: str):
+        _, names = self._edge_vars(paths)
+        em("V " + ", ".join(n + sfx for n in names) + ";")
+        em(f"bool valid{sfx}; int64_t e{sfx}, sn{sfx};")
+
+    def _emit_edge_loads(self, em: _Emitter, paths: List[Path], sfx: str, sbase: str, mask_w: bool):
+        """Issue every global load of one edge iteration (slot ``sbase + sub``) into the ``sfx`` register set."""
         sig = self.sig
         S = sig.s_dim
-        em("int64_t s = s0 + sub;")
-        em("const bool valid = s < end;")
-        em("if (!valid) s = beg;")
-        em("const int64_t e = perm ? perm[s] : s;")
-        em("const int64_t sn = src[e];")
-        # harmonics of this edge, splatted over the channel vector
-        yused = sorted({p.yoff + j for p in paths for j in range(2 * p.l2 + 1)})
+        em.block()
+        em(f"int64_t s = {sbase} + sub;")
+        em(f"valid{sfx} = s < end;")
+        em(f"if (!valid{sfx}) s = beg;")
+        em(f"e{sfx} = perm ? perm[s] : s;")
+        em(f"sn{sfx} = src[e{sfx}];")
+        yused, _ = self._edge_vars(paths)
         for j in yused:
-            em(f"const V y{j} = vsplat(__ldg(y + e * {S} + {j}));")
-        # x chunks
+            em(f"y{j}{sfx} = vsplat(__ldg(y + e{sfx} * {S} + {j}));")
         for i1 in sorted({p.i1 for p in paths}):
             mul, ir = sig.irreps_in1[i1]
             n1 = ir.dim
             xoff = sig.irreps_in1.offsets()[i1]
-            em(f"const T* xp{i1} = x + sn * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
+            em(f"const T* xp{i1} = x + sn{sfx} * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
             for i in range(n1):
-                em(f"const V x{i1}_{i} = vload<{n1}, {mul}>(xp{i1} + {i}, ch0);")
-        # weights
+                em(f"x{i1}_{i}{sfx} = vload<{n1}, {mul}>(xp{i1} + {i}, ch0);")
         for p in paths:
-            zero = "valid" if want_valid_mask_w else "true"
+            zero = f"valid{sfx}" if mask_w else "true"
             al = "true" if (sig.weight_numel % 2 == 0 and p.woff % 2 == 0) else "false"
-            em(f"const V w{p.idx} = vloadw<{p.mul}, {al}>(w + e * {sig.weight_numel} + {p.woff} + ch0, ch0, {zero});")
+            em(f"w{p.idx}{sfx} = vloadw<{p.mul}, {al}>(w + e{sfx} * {sig.weight_numel} + {p.woff} + ch0, ch0, {zero});")
+        em.end()
         return yused
+
+    def _emit_pipelined_loop(self, em: _Emitter, paths: List[Path], body: "_Emitter", mask_w: bool):
+        """Software-pipelined edge loop: the loads of iteration i+1 are in flight while iteration i
+        computes (two explicit register sets A/B, loop unrolled by two, no register moves)."""
+        import re
+
+        _, names = self._edge_vars(paths)
+        pat = re.compile(r"\b(" + "|".join(names + ["valid", "e", "sn"]) + r")\b")
+
+        def emit_body(sfx):
+            em.block()
+            for ln in body.lines:
+                em(pat.sub(lambda m: m.group(1) + sfx, ln))
+            em.end()
+
+        if not self.opts.prefetch:
+            self._emit_edge_decls(em, paths, "")
+            em.block("for (int64_t s0 = beg; s0 < end; s0 += EPW)")
+            self._emit_edge_loads(em, paths, "", "s0", mask_w)
+            emit_body("")
+            em.end()
+            return
+        self._emit_edge_decls(em, paths, "A")
+        self._emit_edge_decls(em, paths, "B")
+        em.block("if (beg < end)")
+        em("int64_t s0 = beg;")
+        self._emit_edge_loads(em, paths, "A", "s0", mask_w)
+        em.block("while (true)")
+        self._emit_edge_loads(em, paths, "B", "(s0 + EPW)", mask_w)
+        emit_body("A")
+        em("s0 += EPW; if (s0 >= end) break;")
+        self._emit_edge_loads(em, paths, "A", "(s0 + EPW)", mask_w)
+        emit_body("B")
+        em("s0 += EPW; if (s0 >= end) break;")
+        em.end()
+        em.end()
 
     # -- forward ---------------------------------------------------------------------
     def _emit_fwd_group(self, em: _Emitter, gid: int, paths: List[Path]):
@@ -315,8 +365,8 @@ class TPGenerator:
         for io in outs:
             n3 = sig.irreps_out[io][1].dim
             em("V " + ", ".join(f"a{io}_{k} = vzero<T>()" for k in range(n3)) + ";")
-        em.block("for (int64_t s0 = beg; s0 < end; s0 += EPW)")
-        self._emit_edge_prologue(em, paths, True)
+        outer = em
+        em = _Emitter()
         for (i1, i2), ps in self._blocks(paths):
             l1, l2 = ps[0].l1, ps[0].l2
             n1 = 2 * l1 + 1
@@ -354,7 +404,8 @@ class TPGenerator:
                         if f"v{p.idx}_{k}" in started:
                             em(f"a{p.io}_{k} = vfma(w{p.idx}, v{p.idx}_{k}, a{p.io}_{k});")
             em.end()
-        em.end()  # edge loop
+        body, em = em, outer
+        self._emit_pipelined_loop(em, paths, body, True)
         # fold edge sub-groups
         em.block("if (EPW > 1)")
         for io in outs:
@@ -394,8 +445,11 @@ class TPGenerator:
             em(f"const T* gp{io} = gout + n * {sig.d_out} + {ooff} + (int64_t)ch0 * {n3};")
             for k in range(n3):
                 em(f"const V g{io}_{k} = vload<{n3}, {mul}>(gp{io} + {k}, ch0);")
-        em.block("for (int64_t s0 = beg; s0 < end; s0 += EPW)")
-        yused = self._emit_edge_prologue(em, paths, False)
+        yused, _ = self._edge_vars(paths)
+        Pq = _pow2ceil(yused[-1] + 1 - yused[0])
+        em(f"const int qbase = er_base<LPE, {Pq}>(cl); const bool qlead = er_leader<LPE, {Pq}>(cl);")
+        outer = em
+        em = _Emitter()
         em("V " + ", ".join(f"q{j} = vzero<T>()" for j in yused) + ";")
         for i1 in sorted({p.i1 for p in paths}):
             n1 = sig.irreps_in1[i1][1].dim
@@ -470,14 +524,19 @@ class TPGenerator:
             for i in range(n1):
                 em(f"vatomic<{n1}, {mul}>(gxp{i1} + {i}, d{i1}_{i}, ch0);")
         em.end()
-        # grad_Y: reduce over the lanes that share this edge, one atomic per component
-        for j in yused:
-            em(f"const T qs{j} = lane_sum<LPE>(vhsum(q{j}));")
-        em.block("if (cl == 0 && valid)")
-        for j in yused:
-            em(f"atomicAdd(gy + e * {S} + {j}, qs{j});")
+        # grad_Y: halving reduce-scatter over the lanes that share this edge, then one atomic per component
+        y0, y1 = yused[0], yused[-1] + 1
+        P = _pow2ceil(y1 - y0)
+        vals = [(f"vhsum(q{j})" if j in yused else "T(0)") for j in range(y0, y1)] + ["T(0)"] * (P - (y1 - y0))
+        em(f"T qv[{P}] = {{{', '.join(vals)}}};")
+        em(f"EdgeReduce<LPE / 2, {P}, T>::run(qv, cl);")
+        em(f"constexpr int QC = ({P} / LPE > 1) ? {P} / LPE : 1;")
+        em.block("if (valid && qlead)")
+        em("#pragma unroll")
+        em(f"for (int j = 0; j < QC; ++j) if (qbase + j < {y1 - y0}) atomicAdd(gy + e * {S} + {y0} + qbase + j, qv[j]);")
         em.end()
-        em.end()  # edge loop
+        body, em = em, outer
+        self._emit_pipelined_loop(em, paths, body, False)
         em.end()
         em()
 

@@ -51,6 +51,9 @@ static int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 extern "C" int nqb_abi_version(void) { return 1; }
+// internal helpers shared with the other translation units of libnqb.so (not part of nqb.h)
+extern "C" int nqb_set_error(const char* msg) { return fail("%s", msg); }
+extern "C" void nqb_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" const char* nqb_last_error(void) { return g_err; }
 extern "C" int64_t nqb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -349,25 +352,6 @@ __global__ void k_sh_bwd(const double* __restrict__ vec, int64_t E, const TO* __
   gvec[3 * e + 1] = (Gy - D * y) * inv;
   gvec[3 * e + 2] = (Gz - D * z) * inv;
 }
-
-#define DISPATCH_LMAX_DTYPE(KERNEL, lmax, dtype, ...)                                   \
-  do {                                                                                  \
-    if (dtype == NQB_F32) {                                                             \
-      switch (lmax) {                                                                   \
-        case 0: KERNEL<0, float> __VA_ARGS__; break;                                    \
-        case 1: KERNEL<1, float> __VA_ARGS__; break;                                    \
-        case 2: KERNEL<2, float> __VA_ARGS__; break;                                    \
-        default: KERNEL<3, float> __VA_ARGS__; break;                                   \
-      }                                                                                 \
-    } else {                                                                            \
-      switch (lmax) {                                                                   \
-        case 0: KERNEL<0, double> __VA_ARGS__; break;                                   \
-        case 1: KERNEL<1, double> __VA_ARGS__; break;                                   \
-        case 2: KERNEL<2, double> __VA_ARGS__; break;                                   \
-        default: KERNEL<3, double> __VA_ARGS__; break;                                  \
-      }                                                                                 \
-    }                                                                                   \
-  } while (0)
 
 extern "C" int nqb_sh_fwd(int lmax, const double* vec, int64_t E, int out_dtype, void* y, nqb_stream_t st) {
   if (lmax < 0 || lmax > 3) return fail("nqb_sh_fwd: lmax=%d unsupported (0..3)", lmax);

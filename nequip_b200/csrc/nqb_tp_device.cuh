@@ -130,4 +130,45 @@ template <int LPE, typename T> __device__ __forceinline__ T lane_sum(T v) {
   return v;
 }
 
+// reduce-scatter of P per-lane partial sums over the LPE lanes that share one edge: halving
+// butterfly (P-1 shuffles instead of P*log2(LPE)).  Afterwards v[0..C) (C = max(1, P/LPE)) hold
+// the edge totals of components er_base(cl) .. er_base(cl)+C; er_leader(cl) picks one lane per
+// component when LPE > P.
+template <int O, int C, typename T> struct EdgeReduce {
+  static __device__ __forceinline__ void run(T* v, int cl) {
+    if constexpr (O >= 1) {
+      if constexpr (C > 1) {
+        constexpr int Hh = C / 2;
+        const bool up = (cl & O) != 0;
+#pragma unroll
+        for (int j = 0; j < Hh; ++j) {
+          const T mine = up ? v[j + Hh] : v[j];
+          const T theirs = up ? v[j] : v[j + Hh];
+          v[j] = mine + __shfl_xor_sync(0xffffffffu, theirs, O);
+        }
+        EdgeReduce<O / 2, Hh, T>::run(v, cl);
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
+        EdgeReduce<O / 2, 1, T>::run(v, cl);
+      }
+    }
+  }
+};
+template <int LPE, int P> __device__ __forceinline__ int er_base(int cl) {
+  int base = 0, c = P;
+#pragma unroll
+  for (int o = LPE / 2; o >= 1; o >>= 1) {
+    if (c > 1) { c >>= 1; if (cl & o) base += c; }
+  }
+  return base;
+}
+template <int LPE, int P> __device__ __forceinline__ bool er_leader(int cl) {
+  int c = P; bool lead = true;
+#pragma unroll
+  for (int o = LPE / 2; o >= 1; o >>= 1) {
+    if (c > 1) c >>= 1; else lead = lead && ((cl & o) == 0);
+  }
+  return lead;
+}
+
 }  // namespace

@@ -188,15 +188,29 @@ class SelfConnection(torch.nn.Module):
         self.weight = torch.nn.Parameter(torch.randn(off))
         self._in_sl = self.irreps_in.slices()
 
-    def forward(self, x, node_attrs):
+    def forward(self, x, node_attrs, types=None, type_table=None):
+        """Generic form: ``node_attrs`` [N, F0].  When the attributes are a per-type table
+        (``node_attrs == type_table[types]``, which is how NequIP builds them,
+        nequip/nn/embedding/node.py:146-175) the bilinear form collapses to one GEMM per irrep
+        pair with the per-type effective weights  Weff[t] = sum_v W[:, v, :] table[t, v]."""
         N = x.shape[0]
         outs: List[Optional[torch.Tensor]] = [None] * len(self.irreps_out)
+        fast = types is not None and type_table is not None
+        if fast:
+            T = type_table.shape[0]
+            onehot = torch.nn.functional.one_hot(types, T).to(x.dtype)  # [N, T]
         for (i, o, off, pw) in self.instr:
             mi, ir = self.irreps_in[i]
             mo = self.irreps_out[o][0]
             W = self.weight[off: off + mi * self.num_attr * mo].view(mi, self.num_attr, mo)
             xi = x[:, self._in_sl[i]].reshape(N, mi, ir.dim)
-            r = pw * torch.einsum("uvw,nuk,nv->nwk", W, xi, node_attrs).reshape(N, mo * ir.dim)
+            if fast:
+                weff = torch.einsum("uvw,tv->tuw", W, type_table).reshape(T * mi, mo) * pw
+                # [N, d, T*mi] @ [T*mi, mo]
+                xe = (onehot.view(N, 1, T, 1) * xi.transpose(1, 2).unsqueeze(2)).reshape(N, ir.dim, T * mi)
+                r = torch.matmul(xe, weff).transpose(1, 2).reshape(N, mo * ir.dim)
+            else:
+                r = pw * torch.einsum("uvw,nuk,nv->nwk", W, xi, node_attrs).reshape(N, mo * ir.dim)
             outs[o] = r if outs[o] is None else outs[o] + r
         for o, (mo, ir) in enumerate(self.irreps_out):
             if outs[o] is None:
@@ -266,12 +280,31 @@ class InteractionBlock(torch.nn.Module):
                                           hidden_layers_width=radial_mlp_width, nonlinearity="silu")
         self.linear_2 = Linear(irreps_mid.simplify(), fout)
         self.sc = SelfConnection(fin, num_node_attrs, fout) if use_sc else None
+        self.use_tensor_core_mlp = True
+        self._prep_mlp = None
 
-    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index):
-        sc = self.sc(x, node_attrs) if self.sc is not None else None
+    def _edge_weights(self, edge_embedding):
+        """Radial MLP.  Depth-1 / width-128 float32 networks whose weights are frozen (inference) run
+        on the tensor cores (tcgen05 3xTF32, nequip_b200/csrc/nqb_mlp.cu); anything else uses the
+        plain torch.mm formulation of the reference (mlp.py:262-268)."""
+        mlp = self.edge_mlp
+        lins = [m for m in mlp.mlp if isinstance(m, ScalarLinearLayer)]
+        frozen = not any(l.weight.requires_grad for l in lins)
+        if (self.use_tensor_core_mlp and frozen and edge_embedding.is_cuda and len(lins) == 2
+                and ops.PreparedRadialMLP.supported(lins[0].in_features, lins[0].out_features, 1,
+                                                    lins[1].out_features, edge_embedding.dtype)):
+            key = (lins[0].weight.data_ptr(), lins[0].weight._version, lins[1].weight.data_ptr(), lins[1].weight._version)
+            if self._prep_mlp is None or self._prep_mlp[0] != key:
+                self._prep_mlp = (key, ops.PreparedRadialMLP(lins[0].weight, float(lins[0].alpha), lins[1].weight,
+                                                             float(lins[1].alpha)))
+            return ops.radial_mlp(edge_embedding, self._prep_mlp[1])
+        return mlp(edge_embedding)
+
+    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index, types=None, type_table=None):
+        sc = self.sc(x, node_attrs, types, type_table) if self.sc is not None else None
         x = self.linear_1(x)
         x = x * self.norm_const
-        w = self.edge_mlp(edge_embedding)
+        w = self._edge_weights(edge_embedding)
         x = self.tp_scatter(x=x, edge_attr=edge_attrs, edge_weight=w, edge_dst=edge_index[0], edge_src=edge_index[1])
         x = self.linear_2(x)
         if sc is not None:
@@ -289,8 +322,8 @@ class ConvNetLayer(torch.nn.Module):
         self.conv = InteractionBlock(prev, edge_attr, conv_out, **conv_kwargs)
         self.irreps_out = layer_out
 
-    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index):
-        x = self.conv(x, node_attrs, edge_attrs, edge_embedding, edge_index)
+    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index, types=None, type_table=None):
+        x = self.conv(x, node_attrs, edge_attrs, edge_embedding, edge_index, types, type_table)
         return self.equivariant_nonlin(x)
 
 
@@ -353,7 +386,7 @@ class NequIPEnergyModel(torch.nn.Module):
             pos, edge_index, shift, cell, lmax=self.l_max, num_bessel=self.num_bessels, r_max=self.r_max,
             poly_p=self.poly_p, prefactor=(2 * math.pi) / (self.r_max * self.r_max), out_dtype=self.model_dtype)
         for layer in self.layers:
-            x = layer(x, node_attrs, edge_attrs, edge_embedding, edge_index)
+            x = layer(x, node_attrs, edge_attrs, edge_embedding, edge_index, types, self.type_embed.weight)
         e_atom = self.readout(x).to(torch.float64)
         if self.scales.numel():
             e_atom = e_atom * self.scales[types]

@@ -322,3 +322,68 @@ def edge_embed(pos, edge_index, shift=None, cell=None, *, lmax: int, num_bessel:
         cell = cell.double().reshape(3, 3).contiguous()
     return _EdgeEmbedFn.apply(pos, edge_index, shift, cell, int(lmax), int(num_bessel), float(r_max),
                               float(poly_p), float(prefactor), out_dtype)
+
+
+# ---------------------------------------------------------------------------------------
+# radial MLP on the tensor cores (tcgen05, 3xTF32)
+# ---------------------------------------------------------------------------------------
+class PreparedRadialMLP:
+    """Second-layer weights of a depth-1 radial MLP, scaled and laid out for the MMA tiles.
+    Inference-only: the weights are treated as constants (no parameter gradients)."""
+
+    HIDDEN = 128
+    NUM_BESSEL = 8
+
+    def __init__(self, W1: torch.Tensor, alpha1: float, W2: torch.Tensor, alpha2: float):
+        _require_cuda(W1, W2)
+        if W1.dtype != torch.float32 or W2.dtype != torch.float32:
+            raise TypeError("PreparedRadialMLP: float32 weights only")
+        if tuple(W1.shape) != (self.NUM_BESSEL, self.HIDDEN) or W2.shape[0] != self.HIDDEN or W2.shape[1] % 32 != 0:
+            raise ValueError(f"PreparedRadialMLP: unsupported shapes {tuple(W1.shape)} / {tuple(W2.shape)}")
+        L = _capi.lib()
+        self.W = int(W2.shape[1])
+        self.w1s = (W1.detach() * alpha1).contiguous()
+        nfl = int(L.nqb_mlp_prepared_bytes(self.W)) // 4
+        self.prep_fwd = torch.empty(nfl, dtype=torch.float32, device=W2.device)
+        self.prep_bwd = torch.empty(nfl, dtype=torch.float32, device=W2.device)
+        W2c = W2.detach().contiguous()
+        _capi.check(L.nqb_mlp_prepare(_ptr(W2c), float(alpha2), self.HIDDEN, self.W, _ptr(self.prep_fwd),
+                                      _ptr(self.prep_bwd), _stream()), "nqb_mlp_prepare")
+
+    @staticmethod
+    def supported(num_bessel: int, hidden: int, depth: int, W: int, dtype) -> bool:
+        return num_bessel == 8 and hidden == 128 and depth == 1 and W % 32 == 0 and dtype == torch.float32
+
+
+class _RadialMLPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, prep: PreparedRadialMLP):
+        L = _capi.lib()
+        E = emb.shape[0]
+        out = torch.empty((E, prep.W), dtype=torch.float32, device=emb.device)
+        _capi.check(L.nqb_mlp_fwd(_ptr(emb), _ptr(prep.w1s), _ptr(prep.prep_fwd), E, prep.NUM_BESSEL, prep.HIDDEN,
+                                  prep.W, _ptr(out), _stream()), "nqb_mlp_fwd")
+        ctx.prep = prep
+        ctx.save_for_backward(emb)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gw):
+        (emb,) = ctx.saved_tensors
+        prep = ctx.prep
+        L = _capi.lib()
+        E = emb.shape[0]
+        gemb = torch.empty_like(emb)
+        gw = gw.contiguous()
+        _capi.check(L.nqb_mlp_bwd(_ptr(emb), _ptr(prep.w1s), _ptr(prep.prep_bwd), _ptr(gw), E, prep.NUM_BESSEL,
+                                  prep.HIDDEN, prep.W, _ptr(gemb), _stream()), "nqb_mlp_bwd")
+        return gemb, None
+
+
+def radial_mlp(emb: torch.Tensor, prep: PreparedRadialMLP) -> torch.Tensor:
+    """``edge_weight = silu(emb @ W1 a1) @ (W2 a2)`` -> ``[E, W]`` float32."""
+    _require_cuda(emb)
+    if emb.dtype != torch.float32 or emb.dim() != 2 or emb.shape[1] != prep.NUM_BESSEL:
+        raise ValueError("radial_mlp: emb must be float32 [E, 8]")
+    return _RadialMLPFn.apply(emb.contiguous(), prep)

@@ -1,0 +1,177 @@
+"""Spatial decomposition of one frame over GPUs with a per-layer halo exchange (host side).
+
+The reference's only sharded-inference design is LAMMPS domain decomposition surfaced to the
+model as owned + ghost atoms and a per-layer ghost-feature exchange hook
+(``nequip/nn/_ghost_exchange_base.py:8-57``, ``nequip/nn/_ghost_exchange_lmp_mliap.py:11-64``,
+``nequip/nn/interaction_block.py:159-199``; inputs in the ML-IAP convention,
+``nequip/integrations/lammps_mliap/lmp_mliap_wrapper.py:202-219``).  This module is the
+B200-native equivalent with ``torch.distributed`` (NCCL over NVLink; gloo in the CPU tests):
+
+* atoms are split into contiguous slabs along x; a rank *owns* its slab and additionally
+  holds *ghost* copies of every non-owned atom that is the source of an edge whose
+  destination it owns -- so every scatter destination is local and the TP+scatter kernel
+  never crosses ranks;
+* before every interaction layer >= 1 the owners' current features are sent to the ranks
+  that hold ghosts of them (``all_to_all_single`` with split sizes); the backward of that
+  exchange is the transposed exchange with accumulation into the owner rows (what LAMMPS'
+  ``reverse_exchange`` does);
+* energies: sum over owned atoms then one all-reduce; forces: each rank's d E_local / d pos
+  over its owned + ghost atoms is scattered into a global ``[N, 3]`` buffer and all-reduced.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ShardPlan:
+    rank: int
+    world: int
+    num_global: int
+    owned: torch.Tensor  # [n_own] global ids (ascending)
+    ghosts: torch.Tensor  # [n_ghost] global ids, grouped by owner rank (ascending rank, then id)
+    local_ids: torch.Tensor  # [n_own + n_ghost] global ids of the local numbering
+    edge_index: torch.Tensor  # [2, E_loc] local numbering; dst (row 0) always < n_own
+    edge_ids: torch.Tensor  # [E_loc] positions in the global edge list
+    send_idx: torch.Tensor  # [sum send] local owned indices to send, grouped by destination rank
+    send_splits: List[int]
+    recv_splits: List[int]  # ghosts received from each rank (matches the grouping of ``ghosts``)
+
+    @property
+    def n_own(self) -> int:
+        return int(self.owned.numel())
+
+    @property
+    def n_ghost(self) -> int:
+        return int(self.ghosts.numel())
+
+
+def slab_owner(pos: torch.Tensor, world: int, axis: int = 0) -> torch.Tensor:
+    """Owner rank of every atom: equal-count slabs along ``axis`` (stable in atom order)."""
+    N = pos.shape[0]
+    order = torch.argsort(pos[:, axis], stable=True)
+    owner = torch.empty(N, dtype=torch.long)
+    bounds = [(N * r) // world for r in range(world + 1)]
+    for r in range(world):
+        owner[order[bounds[r]: bounds[r + 1]]] = r
+    return owner
+
+
+def make_plans(edge_index: torch.Tensor, owner: torch.Tensor, world: int) -> List[ShardPlan]:
+    """All ranks' plans from the global edge list (host-side preprocessing, like the neighbour list).
+    ``edge_index[0]`` = destination/centre, ``edge_index[1]`` = source/neighbour."""
+    N = owner.numel()
+    dst, src = edge_index[0], edge_index[1]
+    plans: List[ShardPlan] = []
+    need: List[List[torch.Tensor]] = [[None] * world for _ in range(world)]  # need[r][s]: ids owned by s that r ghosts
+    owned_ids, ghost_ids, edges, eids = [], [], [], []
+    for r in range(world):
+        own = torch.nonzero(owner == r).view(-1)
+        emask = owner[dst] == r
+        e_ids = torch.nonzero(emask).view(-1)
+        s_glob = src[e_ids]
+        gsrc = torch.unique(s_glob[owner[s_glob] != r])
+        # group ghosts by owner rank
+        gowner = owner[gsrc]
+        order = torch.argsort(gowner * (N + 1) + gsrc)
+        gsrc = gsrc[order]
+        for s in range(world):
+            need[r][s] = gsrc[owner[gsrc] == s]
+        owned_ids.append(own)
+        ghost_ids.append(gsrc)
+        eids.append(e_ids)
+    for r in range(world):
+        own, gh = owned_ids[r], ghost_ids[r]
+        local_ids = torch.cat([own, gh])
+        g2l = torch.full((N,), -1, dtype=torch.long)
+        g2l[local_ids] = torch.arange(local_ids.numel())
+        e_ids = eids[r]
+        ei = torch.stack([g2l[dst[e_ids]], g2l[src[e_ids]]])
+        assert int(ei.min()) >= 0 and (int(ei[0].max()) < own.numel() if e_ids.numel() else True)
+        send_lists = [need[s][r] for s in range(world)]  # what rank s needs from me
+        send_idx = torch.cat([g2l[t] for t in send_lists]) if world > 0 else torch.empty(0, dtype=torch.long)
+        plans.append(
+            ShardPlan(
+                rank=r, world=world, num_global=N, owned=own, ghosts=gh, local_ids=local_ids, edge_index=ei,
+                edge_ids=e_ids, send_idx=send_idx, send_splits=[int(t.numel()) for t in send_lists],
+                recv_splits=[int(need[r][s].numel()) for s in range(world)],
+            )
+        )
+    return plans
+
+
+def shard_data(data: Dict[str, torch.Tensor], plan: ShardPlan) -> Dict[str, torch.Tensor]:
+    """AtomicDataDict-shaped local view: owned atoms first, then ghosts (ML-IAP convention)."""
+    out = {
+        "pos": data["pos"][plan.local_ids],
+        "atom_types": data["atom_types"][plan.local_ids],
+        "edge_index": plan.edge_index,
+    }
+    if "cell" in data:
+        out["cell"] = data["cell"]
+        out["edge_cell_shift"] = data["edge_cell_shift"][plan.edge_ids]
+    return out
+
+
+class _HaloExchangeFn(torch.autograd.Function):
+    """x_own [n_own, D] -> x_full [n_own + n_ghost, D]; backward adds ghost grads into the owners."""
+
+    @staticmethod
+    def forward(ctx, x_own, send_idx, send_splits, recv_splits, group):
+        ctx.send_idx, ctx.send_splits, ctx.recv_splits, ctx.group = send_idx, send_splits, recv_splits, group
+        ctx.n_own = x_own.shape[0]
+        send = x_own.index_select(0, send_idx).contiguous()
+        recv = x_own.new_empty((sum(recv_splits),) + tuple(x_own.shape[1:]))
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_splits, input_split_sizes=send_splits, group=group)
+        return torch.cat([x_own, recv], dim=0)
+
+    @staticmethod
+    def backward(ctx, g_full):
+        g_own = g_full[: ctx.n_own].clone()
+        g_ghost = g_full[ctx.n_own:].contiguous()
+        back = g_full.new_empty((sum(ctx.send_splits),) + tuple(g_full.shape[1:]))
+        dist.all_to_all_single(back, g_ghost, output_split_sizes=ctx.send_splits, input_split_sizes=ctx.recv_splits,
+                               group=ctx.group)
+        g_own.index_add_(0, ctx.send_idx, back)
+        return g_own, None, None, None, None
+
+
+class HaloExchange:
+    def __init__(self, plan: ShardPlan, device, group=None):
+        self.plan, self.group = plan, group
+        self.send_idx = plan.send_idx.to(device)
+
+    def __call__(self, x_own: torch.Tensor) -> torch.Tensor:
+        if self.plan.world == 1:
+            return x_own
+        return _HaloExchangeFn.apply(x_own, self.send_idx, self.plan.send_splits, self.plan.recv_splits, self.group)
+
+
+def sharded_energy_forces(model, local: Dict[str, torch.Tensor], plan: ShardPlan, halo: HaloExchange,
+                          reduce_forces: bool = True):
+    """Energy + forces of one frame sharded over ``plan.world`` ranks.
+
+    ``model`` is a ``NequIPEnergyModel``; ``local`` the rank's ``shard_data`` on its device.
+    Returns (total_energy [1] f64 -- identical on all ranks, forces [N_global, 3] f64 or the
+    local gradient when ``reduce_forces`` is False)."""
+    pos = local["pos"].detach().requires_grad_(True)
+    d = dict(local)
+    d["pos"] = pos
+    with torch.enable_grad():
+        e_atom_own = model.energy_owned(d, plan.n_own, halo)
+        e_loc = e_atom_own.sum()
+        (g,) = torch.autograd.grad([e_loc], [pos])
+    e = e_loc.detach().reshape(1).clone()
+    if plan.world > 1:
+        dist.all_reduce(e, group=halo.group)
+    if not reduce_forces:
+        return e, -g
+    f = torch.zeros((plan.num_global, 3), dtype=g.dtype, device=g.device)
+    f.index_add_(0, plan.local_ids.to(g.device), -g)
+    if plan.world > 1:
+        dist.all_reduce(f, group=halo.group)
+    return e, f

@@ -78,8 +78,11 @@ def test_generator_emits_packed_fma_source():
     assert "tp_fwd_kernel" in src and "tp_bwd_kernel" in src and "vfmai(" in src
     assert 'extern "C" int nqb_spec_fwd' in src and sig.canonical() in src
     # every path's weight slice is loaded exactly once in the forward
+    # software-pipelined loop: two register sets (A/B), each path's weight slice loaded into both,
+    # in the forward and in the backward kernel
     for p in sig.paths:
-        assert len(re.findall(rf"const V w{p.idx} = vloadw", src)) == 2  # once fwd, once bwd
+        assert len(re.findall(rf"\bw{p.idx}A = vloadw", src)) == 4
+        assert len(re.findall(rf"\bw{p.idx}B = vloadw", src)) == 2
 
 
 def test_capi_exports_every_declared_symbol():

@@ -94,3 +94,24 @@ def test_permutation_equivariance():
     assert abs(float(out["total_energy"]) - float(out2["total_energy"])) <= 2e-6 * escale
     fscale = float(out["forces"].abs().max())
     assert float((out["forces"][perm.cuda()] - out2["forces"]).abs().max()) <= 2e-5 * fscale
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name", ["water_l2_f32", "li3po4_l2_f64feat", "asi_l3"])
+def test_energy_forces_inference_path_tensor_core_mlp(name):
+    """Frozen parameters (inference): the radial MLP runs on the tcgen05 3xTF32 kernels."""
+    from nequip_b200 import _capi
+
+    model, sysd = _build(name, torch.float32)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    n0 = _capi.launch_count()
+    out = model(D.to_device(sysd, "cuda"))
+    torch.cuda.synchronize()
+    assert all(l.conv._prep_mlp is not None for l in model.layers), "tensor-core MLP path not taken"
+    assert _capi.launch_count() - n0 >= 4 * len(model.layers)
+    e_ref, ea_ref, f_ref = omodel.energy_and_forces(model.state_dict(), model.config, sysd, torch.float32)
+    e, f = out["total_energy"].cpu(), out["forces"].cpu()
+    assert abs(float(e) - float(e_ref)) <= 1e-5 * float(ea_ref.abs().sum()), (float(e), float(e_ref))
+    fscale = float(f_ref.abs().max())
+    assert float((f - f_ref).abs().max()) <= 5e-5 * fscale, float((f - f_ref).abs().max()) / fscale
