@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 6
+CODEGEN_VERSION = 9
 
 
 # ---------------------------------------------------------------------------
@@ -166,10 +166,18 @@ class GenOptions:
     nwarp: int = 4  # warps (= destination nodes) per CTA
     acc_cap: int = 32  # max output components per channel held by one warp (forward)
     acc_cap_bwd: int = 24
-    prefetch: bool = True
+    prefetch: bool = True  # software-pipelined edge loop (loads of edge i+1 in flight during compute of i)
+    idx_ahead: bool = True  # edge/source indices fetched two iterations ahead (breaks the dependent-load chain)
+    min_blocks_fwd: int = 4  # __launch_bounds__ minBlocksPerSM (0 = unset); occupancy beats everything else here
+    min_blocks_bwd: int = 3
+    red_v2: bool = True  # grad_x via red.global.add.v2.f32 (two adjacent floats per atomic)
+    layout: str = "mul_ir"  # node-feature layout of x / out: "mul_ir" (the reference's, e3nn) or
+    #                         "ir_mul" (channel-contiguous: every chunk is [2l+1, mul]; all node-feature
+    #                         traffic becomes unit-stride 8-byte accesses; used between our own kernels)
 
     def tag(self) -> str:
-        return f"w{self.nwarp}_a{self.acc_cap}_b{self.acc_cap_bwd}_p{int(self.prefetch)}"
+        return (f"w{self.nwarp}_a{self.acc_cap}_b{self.acc_cap_bwd}_p{int(self.prefetch)}{int(self.idx_ahead)}"
+                f"_m{self.min_blocks_fwd}{self.min_blocks_bwd}_r{int(self.red_v2)}_{self.layout}")
 
 
 # ---------------------------------------------------------------------------
@@ -258,6 +266,23 @@ class TPGenerator:
         self.fwd_groups = _partition(sig, self.opts.acc_cap)
         self.bwd_groups = _partition(sig, self.opts.acc_cap_bwd)
 
+    def out_ir_mul(self, io: int):
+        """ir_mul placement of output chunk ``io``: the layout is defined over
+        ``irreps_out.simplify()`` (what ``linear_2`` consumes, interaction_block.py:129-138): adjacent
+        chunks of the same irrep form ONE ``[2l+1, M_total]`` block and chunk ``io`` owns the channel
+        range ``[ubase, ubase + mul)`` of it.  Returns (block offset, M_total, ubase)."""
+        irr = self.sig.irreps_out
+        offs = irr.offsets()
+        lo = io
+        while lo > 0 and irr[lo - 1][1] == irr[io][1]:
+            lo -= 1
+        hi = io
+        while hi + 1 < len(irr) and irr[hi + 1][1] == irr[io][1]:
+            hi += 1
+        mtot = sum(irr[q][0] for q in range(lo, hi + 1))
+        ubase = sum(irr[q][0] for q in range(lo, io))
+        return offs[lo], mtot, ubase
+
     def geometry(self, cpt: int):
         """lanes per edge, edges per warp iteration, channel blocks."""
         pairs = (self.mul_max + cpt - 1) // cpt
@@ -288,16 +313,25 @@ class TPGenerator:
         em("V " + ", ".join(n + sfx for n in names) + ";")
         em(f"bool valid{sfx}; int64_t e{sfx}, sn{sfx};")
 
-    def _emit_edge_loads(self, em: _Emitter, paths: List[Path], sfx: str, sbase: str, mask_w: bool):
-        """Issue every global load of one edge iteration (slot ``sbase + sub``) into the ``sfx`` register set."""
-        sig = self.sig
-        S = sig.s_dim
+    def _emit_index_loads(self, em: _Emitter, sfx: str, sbase: str):
         em.block()
         em(f"int64_t s = {sbase} + sub;")
         em(f"valid{sfx} = s < end;")
         em(f"if (!valid{sfx}) s = beg;")
         em(f"e{sfx} = perm ? perm[s] : s;")
         em(f"sn{sfx} = src[e{sfx}];")
+        em.end()
+
+    def _emit_data_loads(self, em: _Emitter, paths: List[Path], sfx: str, mask_w: bool):
+        """Issue the data loads of one edge iteration into the ``sfx`` register set: the streamed
+        weights first (they only need the edge id), then the harmonics, then the gathered x row."""
+        sig = self.sig
+        S = sig.s_dim
+        em.block()
+        for p in paths:
+            zero = f"valid{sfx}" if mask_w else "true"
+            al = "true" if (sig.weight_numel % 2 == 0 and p.woff % 2 == 0) else "false"
+            em(f"w{p.idx}{sfx} = vloadw<{p.mul}, {al}>(w + e{sfx} * {sig.weight_numel} + {p.woff} + ch0, ch0, {zero});")
         yused, _ = self._edge_vars(paths)
         for j in yused:
             em(f"y{j}{sfx} = vsplat(__ldg(y + e{sfx} * {S} + {j}));")
@@ -305,19 +339,22 @@ class TPGenerator:
             mul, ir = sig.irreps_in1[i1]
             n1 = ir.dim
             xoff = sig.irreps_in1.offsets()[i1]
-            em(f"const T* xp{i1} = x + sn{sfx} * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
-            for i in range(n1):
-                em(f"x{i1}_{i}{sfx} = vload<{n1}, {mul}>(xp{i1} + {i}, ch0);")
-        for p in paths:
-            zero = f"valid{sfx}" if mask_w else "true"
-            al = "true" if (sig.weight_numel % 2 == 0 and p.woff % 2 == 0) else "false"
-            em(f"w{p.idx}{sfx} = vloadw<{p.mul}, {al}>(w + e{sfx} * {sig.weight_numel} + {p.woff} + ch0, ch0, {zero});")
+            if self.opts.layout == "ir_mul":
+                al = "true" if (sig.d_in % 2 == 0 and xoff % 2 == 0 and mul % 2 == 0) else "false"
+                em(f"const T* xp{i1} = x + sn{sfx} * {sig.d_in} + {xoff} + ch0;")
+                for i in range(n1):
+                    em(f"x{i1}_{i}{sfx} = vloadc<{mul}, {al}>(xp{i1} + {i * mul}, ch0);")
+            else:
+                em(f"const T* xp{i1} = x + sn{sfx} * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
+                for i in range(n1):
+                    em(f"x{i1}_{i}{sfx} = vload<{n1}, {mul}>(xp{i1} + {i}, ch0);")
         em.end()
-        return yused
 
     def _emit_pipelined_loop(self, em: _Emitter, paths: List[Path], body: "_Emitter", mask_w: bool):
         """Software-pipelined edge loop: the loads of iteration i+1 are in flight while iteration i
-        computes (two explicit register sets A/B, loop unrolled by two, no register moves)."""
+        computes (two explicit register sets A/B, loop unrolled by two, no register moves); with
+        ``idx_ahead`` the edge id / source index of iteration i+2 are fetched during iteration i so the
+        dependent chain perm -> src -> x[src] never stalls the issue of the data loads."""
         import re
 
         _, names = self._edge_vars(paths)
@@ -332,7 +369,8 @@ class TPGenerator:
         if not self.opts.prefetch:
             self._emit_edge_decls(em, paths, "")
             em.block("for (int64_t s0 = beg; s0 < end; s0 += EPW)")
-            self._emit_edge_loads(em, paths, "", "s0", mask_w)
+            self._emit_index_loads(em, "", "s0")
+            self._emit_data_loads(em, paths, "", mask_w)
             emit_body("")
             em.end()
             return
@@ -340,15 +378,30 @@ class TPGenerator:
         self._emit_edge_decls(em, paths, "B")
         em.block("if (beg < end)")
         em("int64_t s0 = beg;")
-        self._emit_edge_loads(em, paths, "A", "s0", mask_w)
-        em.block("while (true)")
-        self._emit_edge_loads(em, paths, "B", "(s0 + EPW)", mask_w)
-        emit_body("A")
-        em("s0 += EPW; if (s0 >= end) break;")
-        self._emit_edge_loads(em, paths, "A", "(s0 + EPW)", mask_w)
-        emit_body("B")
-        em("s0 += EPW; if (s0 >= end) break;")
-        em.end()
+        if not self.opts.idx_ahead:
+            self._emit_index_loads(em, "A", "s0")
+            self._emit_data_loads(em, paths, "A", mask_w)
+            em.block("while (true)")
+            for cur, nxt in (("A", "B"), ("B", "A")):
+                self._emit_index_loads(em, nxt, "(s0 + EPW)")
+                self._emit_data_loads(em, paths, nxt, mask_w)
+                emit_body(cur)
+                em("s0 += EPW; if (s0 >= end) break;")
+            em.end()
+        else:
+            em("bool validN; int64_t eN, snN;")
+            self._emit_index_loads(em, "N", "s0")
+            em("validA = validN; eA = eN; snA = snN;")
+            self._emit_index_loads(em, "N", "(s0 + EPW)")
+            self._emit_data_loads(em, paths, "A", mask_w)
+            em.block("while (true)")
+            for cur, nxt in (("A", "B"), ("B", "A")):
+                em(f"valid{nxt} = validN; e{nxt} = eN; sn{nxt} = snN;")
+                self._emit_index_loads(em, "N", "(s0 + 2 * EPW)")
+                self._emit_data_loads(em, paths, nxt, mask_w)
+                emit_body(cur)
+                em("s0 += EPW; if (s0 >= end) break;")
+            em.end()
         em.end()
 
     # -- forward ---------------------------------------------------------------------
@@ -418,9 +471,16 @@ class TPGenerator:
             mul, ir = sig.irreps_out[io]
             n3 = ir.dim
             ooff = sig.irreps_out.offsets()[io]
-            em(f"T* op{io} = out + n * {sig.d_out} + {ooff} + (int64_t)ch0 * {n3};")
-            for k in range(n3):
-                em(f"vstore<{n3}, {mul}>(op{io} + {k}, a{io}_{k}, ch0);")
+            if self.opts.layout == "ir_mul":
+                boff, mtot, ubase = self.out_ir_mul(io)
+                al = "true" if (sig.d_out % 2 == 0 and boff % 2 == 0 and mtot % 2 == 0 and ubase % 2 == 0) else "false"
+                em(f"T* op{io} = out + n * {sig.d_out} + {boff + ubase} + ch0;")
+                for k in range(n3):
+                    em(f"vstorew<{mul}, {al}>(op{io} + {k * mtot}, a{io}_{k}, ch0);")
+            else:
+                em(f"T* op{io} = out + n * {sig.d_out} + {ooff} + (int64_t)ch0 * {n3};")
+                for k in range(n3):
+                    em(f"vstore<{n3}, {mul}>(op{io} + {k}, a{io}_{k}, ch0);")
         em.end()
         em.end()
         em()
@@ -442,9 +502,16 @@ class TPGenerator:
             mul, ir = sig.irreps_out[io]
             n3 = ir.dim
             ooff = sig.irreps_out.offsets()[io]
-            em(f"const T* gp{io} = gout + n * {sig.d_out} + {ooff} + (int64_t)ch0 * {n3};")
-            for k in range(n3):
-                em(f"const V g{io}_{k} = vload<{n3}, {mul}>(gp{io} + {k}, ch0);")
+            if self.opts.layout == "ir_mul":
+                boff, mtot, ubase = self.out_ir_mul(io)
+                al = "true" if (sig.d_out % 2 == 0 and boff % 2 == 0 and mtot % 2 == 0 and ubase % 2 == 0) else "false"
+                em(f"const T* gp{io} = gout + n * {sig.d_out} + {boff + ubase} + ch0;")
+                for k in range(n3):
+                    em(f"const V g{io}_{k} = vloadc<{mul}, {al}>(gp{io} + {k * mtot}, ch0);")
+            else:
+                em(f"const T* gp{io} = gout + n * {sig.d_out} + {ooff} + (int64_t)ch0 * {n3};")
+                for k in range(n3):
+                    em(f"const V g{io}_{k} = vload<{n3}, {mul}>(gp{io} + {k}, ch0);")
         yused, _ = self._edge_vars(paths)
         Pq = _pow2ceil(yused[-1] + 1 - yused[0])
         em(f"const int qbase = er_base<LPE, {Pq}>(cl); const bool qlead = er_leader<LPE, {Pq}>(cl);")
@@ -520,9 +587,19 @@ class TPGenerator:
             mul, ir = sig.irreps_in1[i1]
             n1 = ir.dim
             xoff = sig.irreps_in1.offsets()[i1]
+            if self.opts.layout == "ir_mul":
+                al = "true" if (self.opts.red_v2 and sig.d_in % 2 == 0 and xoff % 2 == 0 and mul % 2 == 0) else "false"
+                em(f"T* gxp{i1} = gx + sn * {sig.d_in} + {xoff} + ch0;")
+                for i in range(n1):
+                    em(f"vatomicc<{mul}, {al}>(gxp{i1} + {i * mul}, d{i1}_{i}, ch0);")
+                continue
             em(f"T* gxp{i1} = gx + sn * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
-            for i in range(n1):
-                em(f"vatomic<{n1}, {mul}>(gxp{i1} + {i}, d{i1}_{i}, ch0);")
+            if self.opts.red_v2 and sig.d_in % 2 == 0 and xoff % 2 == 0:
+                args = ", ".join(f"d{i1}_{i}" for i in range(n1))
+                em(f"vatomic_row<{n1}, {mul}>(gxp{i1}, ch0, {args});")
+            else:
+                for i in range(n1):
+                    em(f"vatomic<{n1}, {mul}>(gxp{i1} + {i}, d{i1}_{i}, ch0);")
         em.end()
         # grad_Y: halving reduce-scatter over the lanes that share this edge, then one atomic per component
         y0, y1 = yused[0], yused[-1] + 1
@@ -572,11 +649,13 @@ class TPGenerator:
             self._emit_fwd_group(em, gid, ps)
         for gid, ps in enumerate(self.bwd_groups):
             self._emit_bwd_group(em, gid, ps)
+        mbf = f", {self.opts.min_blocks_fwd}" if self.opts.min_blocks_fwd else ""
+        mbb = f", {self.opts.min_blocks_bwd}" if self.opts.min_blocks_bwd else ""
         # unwritten output chunks (irreps_out entries no instruction writes) must be zero-filled
         unwritten = [io for io in range(len(sig.irreps_out)) if io not in sig.written_outs]
         # kernels
         em.block(
-            "template <typename T> __global__ void __launch_bounds__(32 * NWARP) tp_fwd_kernel("
+            f"template <typename T> __global__ void __launch_bounds__(32 * NWARP{mbf}) tp_fwd_kernel("
             "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
             "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
             "const int64_t* __restrict__ src, int64_t N, T* __restrict__ out)"
@@ -604,7 +683,7 @@ class TPGenerator:
         em.end()
         em()
         em.block(
-            "template <typename T, bool WANT_GX> __global__ void __launch_bounds__(32 * NWARP) tp_bwd_kernel("
+            f"template <typename T, bool WANT_GX> __global__ void __launch_bounds__(32 * NWARP{mbb}) tp_bwd_kernel("
             "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
             "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
             "const int64_t* __restrict__ src, const T* __restrict__ gout, int64_t N, "

@@ -61,6 +61,62 @@ template <int N, int MUL> __device__ __forceinline__ void vatomic(double* p, dou
   if (full || ch0 < MUL) atomicAdd(p, v);
 }
 
+// ---- channel-contiguous (ir_mul) accesses: the CPT channels of one component are adjacent ----------
+template <int MUL, bool AL2> __device__ __forceinline__ float2 vloadc(const float* __restrict__ p, int ch0) {
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  if (full && AL2) return __ldg(reinterpret_cast<const float2*>(p));
+  return make_float2((full || ch0 < MUL) ? __ldg(p) : 0.f, (full || ch0 + 1 < MUL) ? __ldg(p + 1) : 0.f);
+}
+template <int MUL, bool AL2> __device__ __forceinline__ double vloadc(const double* __restrict__ p, int ch0) {
+  constexpr bool full = (MUL % VT<double>::LPE) == 0;
+  return (full || ch0 < MUL) ? __ldg(p) : 0.0;
+}
+__device__ __forceinline__ void red_v2(float* p, float a, float b);
+template <int MUL, bool AL2> __device__ __forceinline__ void vatomicc(float* p, float2 v, int ch0) {
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  if (full && AL2) {
+    red_v2(p, v.x, v.y);
+  } else {
+    if (full || ch0 < MUL) atomicAdd(p, v.x);
+    if (full || ch0 + 1 < MUL) atomicAdd(p + 1, v.y);
+  }
+}
+template <int MUL, bool AL2> __device__ __forceinline__ void vatomicc(double* p, double v, int ch0) {
+  constexpr bool full = (MUL % VT<double>::LPE) == 0;
+  if (full || ch0 < MUL) atomicAdd(p, v);
+}
+
+// whole row of a channel pair: 2*N adjacent floats starting at p (8-byte aligned) -> N vector
+// reductions red.global.add.v2.f32 instead of 2*N scalar ones
+__device__ __forceinline__ void red_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+template <int N, int MUL, typename... Vs> __device__ __forceinline__ void vatomic_row(float* p, int ch0, Vs... vs) {
+  static_assert(sizeof...(Vs) == N, "one value per component");
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  const float2 v[N] = {vs...};
+  if (full) {
+    float flat[2 * N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { flat[i] = v[i].x; flat[N + i] = v[i].y; }
+#pragma unroll
+    for (int q = 0; q < N; ++q) red_v2(p + 2 * q, flat[2 * q], flat[2 * q + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (ch0 < MUL) atomicAdd(p + i, v[i].x);
+      if (ch0 + 1 < MUL) atomicAdd(p + N + i, v[i].y);
+    }
+  }
+}
+template <int N, int MUL, typename... Vs> __device__ __forceinline__ void vatomic_row(double* p, int ch0, Vs... vs) {
+  constexpr bool full = (MUL % VT<double>::LPE) == 0;
+  const double v[N] = {vs...};
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (full || ch0 < MUL) atomicAdd(p + i, v[i]);
+}
+
 // ---- contiguous per-channel scalars (the radial weights): streamed, never re-read -------
 __device__ __forceinline__ float2 ld_stream2(const float* p) {
   float2 r;

@@ -211,3 +211,33 @@ def build_tp_instructions(feature_irreps_in, irreps_edge_attr, feature_irreps_ou
     mid_sorted, p, _ = Irreps(mid).sort()
     ins = [(a, b, p[c], mode, tr) for a, b, c, mode, tr in ins]
     return mid_sorted, ins
+
+
+def mul_ir_to_ir_mul(x, irreps):
+    """``nequip/nn/utils.py:136-155``: [..., mul, 2l+1] chunks -> [..., 2l+1, mul] chunks."""
+    import torch
+
+    irreps = Irreps(irreps)
+    base = x.shape[:-1]
+    out = []
+    for sl, (mul, ir) in zip(irreps.slices(), irreps):
+        ch = x[..., sl]
+        if mul > 1 and ir.dim > 1:
+            ch = ch.reshape(*base, mul, ir.dim).transpose(-1, -2).reshape(*base, mul * ir.dim)
+        out.append(ch)
+    return torch.cat(out, dim=-1).contiguous()
+
+
+def ir_mul_to_mul_ir(x, irreps):
+    """``nequip/nn/utils.py:158-177``."""
+    import torch
+
+    irreps = Irreps(irreps)
+    base = x.shape[:-1]
+    out = []
+    for sl, (mul, ir) in zip(irreps.slices(), irreps):
+        ch = x[..., sl]
+        if mul > 1 and ir.dim > 1:
+            ch = ch.reshape(*base, ir.dim, mul).transpose(-1, -2).reshape(*base, mul * ir.dim)
+        out.append(ch)
+    return torch.cat(out, dim=-1).contiguous()

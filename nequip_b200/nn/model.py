@@ -129,8 +129,9 @@ class Linear(torch.nn.Module):
     """e3nn ``o3.Linear(irreps_in, irreps_out)`` (internal shared weights, no bias,
     path_normalization="element"): out_b = (1/sqrt(sum_a mul_a)) sum_a x_a W_ab over equal irreps."""
 
-    def __init__(self, irreps_in, irreps_out):
+    def __init__(self, irreps_in, irreps_out, layout: str = "mul_ir"):
         super().__init__()
+        self.layout = layout
         self.irreps_in, self.irreps_out = Irreps(irreps_in), Irreps(irreps_out)
         self.instr: List[Tuple[int, int, int, float]] = []  # (i_in, i_out, weight offset, path weight)
         off = 0
@@ -155,9 +156,13 @@ class Linear(torch.nn.Module):
             mi, ir = self.irreps_in[i]
             mo = self.irreps_out[o][0]
             W = self.weight[off: off + mi * mo].view(mi, mo) * pw
-            xi = x[:, self._in_sl[i]].reshape(N, mi, ir.dim)
-            # [N, d, mi] @ [mi, mo] -> [N, d, mo] -> [N, mo, d]
-            r = torch.matmul(xi.transpose(1, 2), W).transpose(1, 2).reshape(N, mo * ir.dim)
+            if self.layout == "ir_mul":
+                # chunk = [d, mi] per node: one GEMM over all (node, component) rows
+                r = torch.matmul(x[:, self._in_sl[i]].reshape(N * ir.dim, mi), W).reshape(N, ir.dim * mo)
+            else:
+                xi = x[:, self._in_sl[i]].reshape(N, mi, ir.dim)
+                # [N, d, mi] @ [mi, mo] -> [N, d, mo] -> [N, mo, d]
+                r = torch.matmul(xi.transpose(1, 2), W).transpose(1, 2).reshape(N, mo * ir.dim)
             outs[o] = r if outs[o] is None else outs[o] + r
         for o, (mo, ir) in enumerate(self.irreps_out):
             if outs[o] is None:
@@ -169,8 +174,9 @@ class SelfConnection(torch.nn.Module):
     """e3nn ``FullyConnectedTensorProduct(feature_irreps_in, F0 x 0e, feature_irreps_out)``
     (interaction_block.py:140-146): out_b[w,k] = (1/sqrt(sum_a mul_a F0)) sum_a sum_uv W_ab[u,v,w] x_a[u,k] attr[v]."""
 
-    def __init__(self, irreps_in, num_attr: int, irreps_out):
+    def __init__(self, irreps_in, num_attr: int, irreps_out, layout: str = "mul_ir"):
         super().__init__()
+        self.layout = layout
         self.irreps_in, self.irreps_out, self.num_attr = Irreps(irreps_in), Irreps(irreps_out), num_attr
         pairs = [
             (i, o)
@@ -203,6 +209,16 @@ class SelfConnection(torch.nn.Module):
             mi, ir = self.irreps_in[i]
             mo = self.irreps_out[o][0]
             W = self.weight[off: off + mi * self.num_attr * mo].view(mi, self.num_attr, mo)
+            if self.layout == "ir_mul":
+                xk = x[:, self._in_sl[i]].reshape(N, ir.dim, mi)  # [N, d, mi]
+                if fast:
+                    weff = torch.einsum("uvw,tv->tuw", W, type_table).reshape(T * mi, mo) * pw
+                    xe = (onehot.view(N, 1, T, 1) * xk.unsqueeze(2)).reshape(N * ir.dim, T * mi)
+                    r = torch.matmul(xe, weff).reshape(N, ir.dim * mo)
+                else:
+                    r = pw * torch.einsum("uvw,nku,nv->nkw", W, xk, node_attrs).reshape(N, ir.dim * mo)
+                outs[o] = r if outs[o] is None else outs[o] + r
+                continue
             xi = x[:, self._in_sl[i]].reshape(N, mi, ir.dim)
             if fast:
                 weff = torch.einsum("uvw,tv->tuw", W, type_table).reshape(T * mi, mo) * pw
@@ -221,8 +237,9 @@ class SelfConnection(torch.nn.Module):
 class Gate(torch.nn.Module):
     """e3nn ``nn.Gate`` with normalize2mom'd SiLU (even) / tanh (odd) (convnetlayer.py:42-56,104-112)."""
 
-    def __init__(self, irreps_scalars, irreps_gates, irreps_gated):
+    def __init__(self, irreps_scalars, irreps_gates, irreps_gated, layout: str = "mul_ir"):
         super().__init__()
+        self.layout = layout
         self.irreps_scalars, self.irreps_gates, self.irreps_gated = (
             Irreps(irreps_scalars), Irreps(irreps_gates), Irreps(irreps_gated))
         self.irreps_in = self.irreps_scalars + self.irreps_gates + self.irreps_gated
@@ -251,8 +268,12 @@ class Gate(torch.nn.Module):
             off = ns + ng
             g0 = 0
             for mul, ir in self.irreps_gated:
-                ch = x[:, off: off + mul * ir.dim].reshape(N, mul, ir.dim)
-                parts.append((ch * gates[:, g0: g0 + mul].unsqueeze(-1)).reshape(N, mul * ir.dim))
+                if self.layout == "ir_mul":
+                    ch = x[:, off: off + mul * ir.dim].reshape(N, ir.dim, mul)
+                    parts.append((ch * gates[:, g0: g0 + mul].unsqueeze(1)).reshape(N, mul * ir.dim))
+                else:
+                    ch = x[:, off: off + mul * ir.dim].reshape(N, mul, ir.dim)
+                    parts.append((ch * gates[:, g0: g0 + mul].unsqueeze(-1)).reshape(N, mul * ir.dim))
                 off += mul * ir.dim
                 g0 += mul
         return torch.cat(parts, dim=1)
@@ -266,20 +287,22 @@ class InteractionBlock(torch.nn.Module):
 
     def __init__(self, feature_irreps_in, irreps_edge_attr, feature_irreps_out, num_edge_embed: int,
                  num_node_attrs: int, radial_mlp_depth: int, radial_mlp_width: int, use_sc: bool,
-                 avg_num_neighbors: float):
+                 avg_num_neighbors: float, is_first_layer: bool = False, layout: str = "mul_ir"):
         super().__init__()
+        self.is_first_layer = is_first_layer
+        self.layout = layout
         fin, fe, fout = Irreps(feature_irreps_in), Irreps(irreps_edge_attr), Irreps(feature_irreps_out)
         self.feature_irreps_in, self.irreps_edge_attr, self.feature_irreps_out = fin, fe, fout
         self.register_buffer("norm_const", torch.tensor(1.0 / math.sqrt(avg_num_neighbors)), persistent=False)
-        self.linear_1 = Linear(fin, fin)
+        self.linear_1 = Linear(fin, fin, layout)
         irreps_mid, instructions = build_tp_instructions(fin, fe, fout)
         self.irreps_mid, self.instructions = irreps_mid, instructions
-        self.tp_scatter = B200TensorProductScatter(fin, fe, irreps_mid, instructions)
+        self.tp_scatter = B200TensorProductScatter(fin, fe, irreps_mid, instructions, layout=layout)
         self.edge_mlp = ScalarMLPFunction(num_edge_embed, self.tp_scatter.weight_numel,
                                           hidden_layers_depth=radial_mlp_depth,
                                           hidden_layers_width=radial_mlp_width, nonlinearity="silu")
-        self.linear_2 = Linear(irreps_mid.simplify(), fout)
-        self.sc = SelfConnection(fin, num_node_attrs, fout) if use_sc else None
+        self.linear_2 = Linear(irreps_mid.simplify(), fout, layout)
+        self.sc = SelfConnection(fin, num_node_attrs, fout, layout) if use_sc else None
         self.use_tensor_core_mlp = True
         self._prep_mlp = None
 
@@ -300,12 +323,25 @@ class InteractionBlock(torch.nn.Module):
             return ops.radial_mlp(edge_embedding, self._prep_mlp[1])
         return mlp(edge_embedding)
 
-    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index, types=None, type_table=None):
+    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index, types=None, type_table=None,
+                n_own: Optional[int] = None, halo=None):
+        """``n_own``/``halo``: sharded frames (owned atoms first, then ghosts).  As in the reference
+        (interaction_block.py:159-199) the first layer sees the type embedding of owned + ghost atoms;
+        later layers work on owned rows, refresh the ghosts through ``halo`` right before the
+        TP+scatter and truncate to the owned rows right after it."""
+        if n_own is not None and not self.is_first_layer:
+            x = x[:n_own]
+            node_attrs = node_attrs[:n_own]
+            types = None if types is None else types[:n_own]
         sc = self.sc(x, node_attrs, types, type_table) if self.sc is not None else None
         x = self.linear_1(x)
         x = x * self.norm_const
+        if halo is not None and not self.is_first_layer:
+            x = halo(x)
         w = self._edge_weights(edge_embedding)
         x = self.tp_scatter(x=x, edge_attr=edge_attrs, edge_weight=w, edge_dst=edge_index[0], edge_src=edge_index[1])
+        if n_own is not None:
+            x = x[:n_own]
         x = self.linear_2(x)
         if sc is not None:
             x = x + sc
@@ -318,12 +354,13 @@ class ConvNetLayer(torch.nn.Module):
     def __init__(self, prev: Irreps, edge_attr: Irreps, hidden: Irreps, **conv_kwargs):
         super().__init__()
         scalars, gates, gated, conv_out, layer_out = gate_irreps(prev, edge_attr, hidden)
-        self.equivariant_nonlin = Gate(scalars, gates, gated)
+        self.equivariant_nonlin = Gate(scalars, gates, gated, conv_kwargs.get("layout", "mul_ir"))
         self.conv = InteractionBlock(prev, edge_attr, conv_out, **conv_kwargs)
         self.irreps_out = layer_out
 
-    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index, types=None, type_table=None):
-        x = self.conv(x, node_attrs, edge_attrs, edge_embedding, edge_index, types, type_table)
+    def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index, types=None, type_table=None,
+                n_own=None, halo=None):
+        x = self.conv(x, node_attrs, edge_attrs, edge_embedding, edge_index, types, type_table, n_own, halo)
         return self.equivariant_nonlin(x)
 
 
@@ -338,10 +375,11 @@ class NequIPEnergyModel(torch.nn.Module):
                  radial_mlp_width: int = 128, num_bessels: int = 8, polynomial_cutoff_p: float = 6.0,
                  avg_num_neighbors: float = 1.0, per_type_energy_scales: Optional[Sequence[float]] = None,
                  per_type_energy_shifts: Optional[Sequence[float]] = None, model_dtype=torch.float32,
-                 seed: int = 123):
+                 seed: int = 123, node_layout: str = "ir_mul"):
         super().__init__()
         self.r_max, self.l_max, self.num_bessels, self.poly_p = float(r_max), l_max, num_bessels, float(polynomial_cutoff_p)
         self.model_dtype = model_dtype
+        self.node_layout = node_layout  # internal layout of node features between the kernels
         self.config = dict(r_max=r_max, type_names=list(type_names), num_layers=num_layers, l_max=l_max, parity=parity,
                            num_features=num_features, radial_mlp_depth=radial_mlp_depth,
                            radial_mlp_width=radial_mlp_width, num_bessels=num_bessels,
@@ -360,7 +398,8 @@ class NequIPEnergyModel(torch.nn.Module):
             for li, h in enumerate(hiddens):
                 layer = ConvNetLayer(prev, edge_attr, h, num_edge_embed=num_bessels, num_node_attrs=num_features,
                                      radial_mlp_depth=radial_mlp_depth, radial_mlp_width=radial_mlp_width,
-                                     use_sc=(li != 0), avg_num_neighbors=avg_num_neighbors)
+                                     use_sc=(li != 0), avg_num_neighbors=avg_num_neighbors,
+                                     is_first_layer=(li == 0), layout=node_layout)
                 layers.append(layer)
                 prev = layer.irreps_out
             self.layers = torch.nn.ModuleList(layers)
@@ -395,6 +434,29 @@ class NequIPEnergyModel(torch.nn.Module):
         data[PER_ATOM_ENERGY_KEY] = e_atom
         data[TOTAL_ENERGY_KEY] = e_atom.sum(dim=0, keepdim=True)
         return data
+
+    def energy_owned(self, data: Dict[str, torch.Tensor], n_own: int, halo) -> torch.Tensor:
+        """Per-atom energies [n_own, 1] f64 of the OWNED atoms of a sharded frame (``data`` holds owned
+        atoms first, then ghosts; every edge's destination is owned) -- see nequip_b200/parallel.py."""
+        pos, edge_index = data[POSITIONS_KEY], data[EDGE_INDEX_KEY]
+        types = data[ATOM_TYPE_KEY].view(-1)
+        node_attrs = self.type_embed(types)
+        x = node_attrs
+        shift, cell = data.get(EDGE_CELL_SHIFT_KEY), data.get(CELL_KEY)
+        if cell is None:
+            shift = None
+        _vec, edge_attrs, edge_embedding = ops.edge_embed(
+            pos, edge_index, shift, cell, lmax=self.l_max, num_bessel=self.num_bessels, r_max=self.r_max,
+            poly_p=self.poly_p, prefactor=(2 * math.pi) / (self.r_max * self.r_max), out_dtype=self.model_dtype)
+        for layer in self.layers:
+            x = layer(x, node_attrs, edge_attrs, edge_embedding, edge_index, types, self.type_embed.weight, n_own, halo)
+        e_atom = self.readout(x).to(torch.float64)
+        t_own = types[:n_own]
+        if self.scales.numel():
+            e_atom = e_atom * self.scales[t_own]
+        if self.shifts.numel():
+            e_atom = e_atom + self.shifts[t_own]
+        return e_atom
 
     def forward(self, data: Dict[str, torch.Tensor], compute_forces: bool = True) -> Dict[str, torch.Tensor]:
         data = dict(data)

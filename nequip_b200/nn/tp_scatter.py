@@ -63,6 +63,7 @@ class B200TensorProductScatter(_Base):
         irreps_mid,
         instructions,
         gen_options: Optional[GenOptions] = None,
+        layout: str = "mul_ir",
     ) -> None:
         super().__init__(
             feature_irreps_in=feature_irreps_in,
@@ -72,6 +73,13 @@ class B200TensorProductScatter(_Base):
         )
         # ^ with nequip installed the base class keeps `self.tp` (and its persistent buffers)
         # around so that state dicts load with or without this modifier applied
+        # layout="mul_ir" is the reference's (e3nn) node-feature layout and the drop-in default;
+        # "ir_mul" (channel-contiguous, what cuEquivariance uses, nequip/nn/_tp_scatter_cueq.py:107-122)
+        # is used between our own kernels
+        import dataclasses
+
+        gen_options = dataclasses.replace(gen_options or GenOptions(), layout=layout)
+        self.layout = layout
         self._plan = ops.get_plan(
             Irreps(feature_irreps_in), Irreps(irreps_edge_attr), Irreps(irreps_mid), instructions, gen_options
         )

@@ -33,7 +33,7 @@ def _oracle(sig, x, y, w, dst, src):
     )
 
 
-def _run_case(sig, dtype, N, E, seed=0, sort_edges=False, dst_hi=None, scale_check=True):
+def _run_case(sig, dtype, N, E, seed=0, sort_edges=False, dst_hi=None, scale_check=True, layout="mul_ir"):
     dev = "cuda"
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(N, sig.d_in, generator=g, dtype=torch.float64)
@@ -50,10 +50,17 @@ def _run_case(sig, dtype, N, E, seed=0, sort_edges=False, dst_hi=None, scale_che
     torch.set_default_dtype(dtype)
     try:
         mod = B200TensorProductScatter(
-            sig.irreps_in1, sig.irreps_in2, sig.irreps_out, [(a, b, c, "uvu", True) for a, b, c in sig.instructions]
+            sig.irreps_in1, sig.irreps_in2, sig.irreps_out, [(a, b, c, "uvu", True) for a, b, c in sig.instructions],
+            layout=layout,
         )
     finally:
         torch.set_default_dtype(prev)
+    from nequip_b200.irreps import ir_mul_to_mul_ir, mul_ir_to_ir_mul
+
+    # ir_mul: node features are channel-contiguous; the output layout is defined over irreps_mid.simplify()
+    to_k = (lambda t, irr: mul_ir_to_ir_mul(t, irr)) if layout == "ir_mul" else (lambda t, irr: t)
+    from_k = (lambda t, irr: ir_mul_to_mul_ir(t, irr)) if layout == "ir_mul" else (lambda t, irr: t)
+    out_irr = sig.irreps_out.simplify()
 
     # oracle (float64, CPU)
     xo, yo, wo = (t.clone().requires_grad_(True) for t in (x, y, w))
@@ -61,13 +68,17 @@ def _run_case(sig, dtype, N, E, seed=0, sort_edges=False, dst_hi=None, scale_che
     gxo, gyo, gwo = torch.autograd.grad(out_o, [xo, yo, wo], gout)
 
     # kernel
-    xk, yk, wk = (t.to(dev, dtype).requires_grad_(True) for t in (x, y, w))
+    xk = to_k(x, sig.irreps_in1).to(dev, dtype).requires_grad_(True)
+    yk, wk = (t.to(dev, dtype).requires_grad_(True) for t in (y, w))
     out_k = mod(xk, yk, wk, dst.to(dev), src.to(dev))
     assert out_k.shape == (N, sig.d_out) and out_k.dtype == dtype
     tol = TOL[dtype]
-    torch.testing.assert_close(out_k.detach().cpu().double(), out_o.detach(), atol=tol, rtol=tol)
+    torch.testing.assert_close(from_k(out_k.detach().cpu().double(), out_irr), out_o.detach(), atol=tol, rtol=tol)
+    gout_k = to_k(gout, out_irr).to(dev, dtype)
     for name, inp, ref in (("x", xk, gxo), ("edge_attr", yk, gyo), ("edge_weight", wk, gwo)):
-        (gk,) = torch.autograd.grad(out_k, inp, gout.to(dev, dtype), retain_graph=True)
+        (gk,) = torch.autograd.grad(out_k, inp, gout_k, retain_graph=True)
+        if name == "x":
+            gk = from_k(gk.cpu(), sig.irreps_in1)
         # gradients of sums over E*paths terms: scale tolerance like assert_close does (atol + rtol*|ref|)
         torch.testing.assert_close(gk.cpu().double(), ref, atol=tol * (10 if dtype == torch.float32 else 1), rtol=tol,
                                    msg=lambda m: f"grad wrt {name}: {m}")
@@ -76,10 +87,11 @@ def _run_case(sig, dtype, N, E, seed=0, sort_edges=False, dst_hi=None, scale_che
 _GRID = ks.reference_test_grid()
 
 
+@pytest.mark.parametrize("layout", ["mul_ir", "ir_mul"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
 @pytest.mark.parametrize("idx", range(len(_GRID)))
-def test_reference_grid(idx, dtype):
-    _run_case(_GRID[idx], dtype, NUM_NODES, NUM_EDGES, seed=idx)
+def test_reference_grid(idx, dtype, layout):
+    _run_case(_GRID[idx], dtype, NUM_NODES, NUM_EDGES, seed=idx, layout=layout)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
@@ -89,6 +101,7 @@ def test_model_layer_shapes(cfg, dtype):
     lmax, nf, nl = cfg
     for li, sig in enumerate(ks.nequip_layer_signatures(lmax, nf, nl)):
         _run_case(sig, dtype, N=23, E=301, seed=100 + li, sort_edges=True)
+        _run_case(sig, dtype, N=23, E=301, seed=100 + li, sort_edges=True, layout="ir_mul")
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])

@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Time generator variants (GenOptions) of the fused TP kernels on one workload's layer signatures.
+`--build-only` compiles every variant (CPU box); on the GPU box the prebuilt libraries are timed."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from nequip_b200 import build  # noqa: E402
+from nequip_b200.codegen import GenOptions  # noqa: E402
+from nequip_b200.known_signatures import nequip_layer_signatures  # noqa: E402
+
+VARIANTS = {
+    "default": GenOptions(),
+    "irmul": GenOptions(layout="ir_mul"),
+    "irmul_nopf": GenOptions(layout="ir_mul", prefetch=False, idx_ahead=False),
+    "irmul_nopf_mb0": GenOptions(layout="ir_mul", prefetch=False, idx_ahead=False, min_blocks_fwd=0, min_blocks_bwd=0),
+    "irmul_pf_mb0": GenOptions(layout="ir_mul", min_blocks_fwd=0, min_blocks_bwd=0),
+    "irmul_mb5": GenOptions(layout="ir_mul", min_blocks_fwd=5, min_blocks_bwd=4),
+    "irmul_nopf_mb5": GenOptions(layout="ir_mul", prefetch=False, idx_ahead=False, min_blocks_fwd=5, min_blocks_bwd=4),
+    "irmul_a16_mb6": GenOptions(layout="ir_mul", acc_cap=16, acc_cap_bwd=12, min_blocks_fwd=6, min_blocks_bwd=4),
+    "irmul_nopf_a16_mb6": GenOptions(layout="ir_mul", prefetch=False, idx_ahead=False, acc_cap=16, acc_cap_bwd=12, min_blocks_fwd=6, min_blocks_bwd=4),
+}
+_OLD = {
+    "nopf": GenOptions(prefetch=False, idx_ahead=False),
+    "pf": GenOptions(prefetch=True, idx_ahead=False),
+    "pf_idx": GenOptions(),
+    "pf_idx_mb4": GenOptions(min_blocks_fwd=4, min_blocks_bwd=3),
+    "pf_idx_a24": GenOptions(acc_cap=24, acc_cap_bwd=16),
+    "pf_idx_a16": GenOptions(acc_cap=16, acc_cap_bwd=12),
+    "nopf_a16": GenOptions(prefetch=False, idx_ahead=False, acc_cap=16, acc_cap_bwd=12),
+    "pf_idx_w2": GenOptions(nwarp=2),
+    "pf_idx_w8": GenOptions(nwarp=8),
+    "pf_idx_nored2": GenOptions(red_v2=False),
+    "nopf_a24_mb": GenOptions(prefetch=False, idx_ahead=False, acc_cap=24, acc_cap_bwd=16, min_blocks_fwd=5, min_blocks_bwd=4),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg", default="2,64,4")
+    ap.add_argument("--layers", default="1,2,3")
+    ap.add_argument("--build-only", action="store_true")
+    ap.add_argument("--variants", default=",".join(VARIANTS))
+    args = ap.parse_args()
+    lm, nf, nl = map(int, args.cfg.split(","))
+    sigs = nequip_layer_signatures(lm, nf, nl)
+    layers = [int(x) for x in args.layers.split(",")]
+    names = args.variants.split(",")
+    todo = [(sigs[li], VARIANTS[v]) for li in layers for v in names]
+    build.ensure_specs(todo)
+    if args.build_only:
+        print("built", len(todo))
+        return
+    from bench import build_system, tp_algorithmic_bytes, load_peaks
+    from nequip_b200 import ops
+
+    peak, _ = load_peaks()
+    wl = {(2, 64): "li3po4_10k_l2_f64", (2, 32): "water_1k_l2_f32", (3, 32): "asi_50k_l3_f32"}[(lm, nf)]
+    sysd, meta, mk = build_system(wl, seed=0)
+    dev = torch.device("cuda")
+    N, E = sysd["pos"].shape[0], sysd["edge_index"].shape[1]
+    ei = sysd["edge_index"].to(dev)
+    csr = ops.build_csr(ei[0].contiguous(), N)
+    src = ei[1].contiguous()
+    L = ops._capi.lib()
+    g = torch.Generator(device=dev).manual_seed(0)
+
+    def timeit(fn, reps=8, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for li in layers:
+        sig = sigs[li]
+        x = torch.randn(N, sig.d_in, device=dev, generator=g)
+        y = torch.randn(E, sig.s_dim, device=dev, generator=g)
+        w = torch.randn(E, sig.weight_numel, device=dev, generator=g)
+        gout = torch.randn(N, sig.d_out, device=dev, generator=g)
+        out = torch.empty(N, sig.d_out, device=dev)
+        gx, gy, gw = torch.zeros_like(x), torch.zeros_like(y), torch.empty_like(w)
+        st = torch.cuda.current_stream().cuda_stream
+        ref_out = None
+        for v in names:
+            plan = ops.TPPlan(sig.irreps_in1, sig.irreps_in2, sig.irreps_out, sig.instructions, VARIANTS[v])
+
+            def fwd():
+                ops._capi.check(L.nqb_tp_scatter_fwd(plan.handle, 0, x.data_ptr(), y.data_ptr(), w.data_ptr(), csr.row_ptr.data_ptr(),
+                                                     0, src.data_ptr(), N, E, out.data_ptr(), st), "fwd")
+
+            def bwd():
+                ops._capi.check(L.nqb_tp_scatter_bwd(plan.handle, 0, x.data_ptr(), y.data_ptr(), w.data_ptr(), csr.row_ptr.data_ptr(),
+                                                     0, src.data_ptr(), gout.data_ptr(), N, E, gx.data_ptr(), gy.data_ptr(),
+                                                     gw.data_ptr(), st), "bwd")
+
+            tf, tb = timeit(fwd), timeit(bwd)
+            if ref_out is None:
+                ref_out = out.clone()
+            dev_max = float((out - ref_out).abs().max())
+            af, ab = tp_algorithmic_bytes(sig, N, E), tp_algorithmic_bytes(sig, N, E, backward=True)
+            print(json.dumps({"layer": li, "variant": v, "fwd_ms": round(tf, 4), "fwd_frac": round(af / tf / 1e6 / peak, 3),
+                              "bwd_ms": round(tb, 4), "bwd_frac": round(ab / tb / 1e6 / peak, 3), "dev_vs_first": dev_max}), flush=True)
+        del x, y, w, gout, out, gx, gy, gw
+
+
+if __name__ == "__main__":
+    main()
