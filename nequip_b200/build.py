@@ -61,13 +61,13 @@ def runtime_lib_path() -> str:
 def ensure_runtime(force: bool = False) -> str:
     """Build (if stale) and return the path of libnqb.so."""
     out = runtime_lib_path()
-    cus = [os.path.join(CSRC, "nqb_runtime.cu"), os.path.join(CSRC, "nqb_mlp.cu")]
-    srcs = cus + [os.path.join(INCLUDE, "nqb.h")]
+    cus = [os.path.join(CSRC, n) for n in ("nqb_runtime.cu", "nqb_mlp.cu", "nqb_gemm.cu")]
+    srcs = cus + [os.path.join(INCLUDE, "nqb.h"), os.path.join(CSRC, "nqb_tc.cuh")]
     with _lock:
         if force or _newer(srcs, out):
             os.makedirs(LIBDIR, exist_ok=True)
             tmp = out + f".tmp{os.getpid()}"
-            _run([nvcc_path(), *ARCH_FLAGS, *COMMON_FLAGS, "-I", INCLUDE, "-o", tmp, *cus, "-ldl"])
+            _run([nvcc_path(), *ARCH_FLAGS, *COMMON_FLAGS, "-I", INCLUDE, "-Xptxas", "-v", "-o", tmp, *cus, "-ldl"])
             os.replace(tmp, out)
     return out
 

@@ -1,0 +1,347 @@
+// Grouped fp32-accurate GEMM on the 5th-gen tensor cores (tcgen05 kind::tf32, 3xTF32 split), sm_100a.
+//
+//   C_p[M, N_p] (ldc)  (+)=  rowscale_p[m] * ( A_p[M, K_p] (lda, fp32 row-major) @ B_p[K_p, N_p] )
+//
+// for a list of problems p that share M (number of edges or atoms) -- one launch per dense layer:
+//   * radial MLP second layer and its backward         nequip/nn/mlp.py:262-268 (torch.mm)
+//   * o3.Linear per-irrep channel mixing (linear_1/2)   nequip/nn/interaction_block.py:82-87,129-138
+//   * self-connection FullyConnectedTensorProduct       nequip/nn/interaction_block.py:140-146
+//     (per-type effective weights; rowscale = one-hot column of the atom type)
+// in the channel-contiguous (ir_mul) node layout every (irrep component, chunk pair) is a plain
+// strided GEMM, so no transposes/copies are needed around these calls.
+//
+// fp32 parity on a TF32 pipe: a = hi + lo (hi = cvt.rna.tf32), D = A_hi B_hi + (A_lo B_hi + A_hi B_lo).
+// The tensor core's fp32 accumulate truncates (measured ~3e-8 relative bias per accumulation
+// step), so the two cross terms go to their own TMEM accumulator and long reductions are cut into
+// segments of SEG_CHUNKS*32 in K whose partial sums are added in registers (round-to-nearest).
+//
+// Roles per CTA (192 threads, persistent over (M-tile, N-tile) work items, N-tile fastest so that
+// the CTAs working on one A tile run together and share it in L2):
+//   warps 0-3  stream the A chunk [128 x 32] through registers (coalesced 16-byte loads), split it
+//              hi/lo into the canonical K-major core-matrix layout in shared memory; flush finished
+//              accumulator segments TMEM -> registers; epilogue through a swizzled staging tile so
+//              that the global stores are full 128-byte rows
+//   warp  4    lane 0: cp.async.bulk of the pre-split weight chunk (+ mbarrier complete_tx)
+//   warp  5    lane 0: tcgen05.mma M=128, N<=128, K=8: 4 k-steps x 3 terms per chunk; tcgen05.commit
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nqb.h"
+#include "nqb_tc.cuh"
+
+namespace {
+
+constexpr int TM = 128;          // rows per tile
+constexpr int TN = 128;          // max columns per tile
+constexpr int KC = 32;           // K chunk
+constexpr int STAGES = 3;
+constexpr int SEG_CHUNKS = 10;   // chunks per accumulation segment (40 accumulate steps on the hi*hi accumulator)
+constexpr int BLOCK_FLOATS = 2 * TN * KC;  // one prepared weight block: [hi | lo] x [128 x 32]
+
+struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
+  int64_t a_off, c_off, b_off, rs_off;  // element offsets from the base pointers (rs_off < 0: no row scale)
+  int64_t lda, ldc, K, N;
+  int64_t kchunks, ntiles, tile0, flags;  // flags bit0: accumulate into C
+};
+
+struct Smem {
+  float a[STAGES][2 * TM * KC];  // 3 x 32 KB
+  float b[STAGES][BLOCK_FLOATS];  // 3 x 32 KB
+  float stage[4][32 * 32];       // epilogue staging, one 32x32 tile per warp (swizzled)
+  uint64_t a_full[STAGES], b_full[STAGES], empty[STAGES];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ const GemmDesc* find_desc(const GemmDesc* d, int nd, int q) {
+  int i = 0;
+  while (i + 1 < nd && d[i + 1].tile0 <= q) ++i;
+  return d + i;
+}
+
+__global__ void __launch_bounds__(192, 1)
+k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const float* __restrict__ a_base,
+         const float* __restrict__ b_base, float* __restrict__ c_base, const float* __restrict__ rs_base, int64_t M) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t mtiles = (M + TM - 1) / TM;
+  const int64_t nwork = mtiles * ntiles_total;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&S.a_full[s], 128); mbar_init(&S.b_full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(&S.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp < 4) {
+    // =========================== A producer / segment flush / epilogue ===============================
+    uint32_t it = 0;    // global chunk counter (stage ring)
+    uint32_t gseg = 0;  // global segment counter (accumulator ring)
+    const int r8 = lane & 7, kq = lane >> 3;
+    const int row = tid;  // accumulator row owned by this thread (TMEM lane)
+    float acc[TN];
+    for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+      const int64_t mt = wi / ntiles_total;
+      const int q = (int)(wi % ntiles_total);
+      const GemmDesc* d = find_desc(descs, ndesc, q);
+      const int nt = q - (int)d->tile0;
+      const int K = (int)d->K, kchunks = (int)d->kchunks;
+      const int64_t lda = d->lda;
+      const float* A = a_base + d->a_off;
+      const int64_t m0 = mt * TM;
+      const int nseg = (kchunks + SEG_CHUNKS - 1) / SEG_CHUNKS;
+      int flushed = 0;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+
+      auto flush = [&](int sidx) {
+        const uint32_t g = gseg + sidx, buf = g & 1;
+        mbar_wait(&S.acc_full[buf], (g >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < TN / 16; ++cb) {
+          float hh[16], xx[16];
+          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + buf * 256 + cb * 16, hh);
+          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + buf * 256 + 128 + cb * 16, xx);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += hh[j] + xx[j];
+        }
+        tc_fence_before();
+        mbar_arrive(&S.acc_empty[buf]);
+      };
+
+      for (int c = 0; c < kchunks; ++c, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        float4 v[8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int64_t m = m0 + warp * 32 + g * 8 + r8;
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {
+            const int k = c * KC + (hp * 4 + kq) * 4;
+            v[g * 2 + hp] = (m < M && k < K) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + k))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (it >= STAGES) mbar_wait(&S.empty[s], ph ^ 1);
+        float* ahi = S.a[s];
+        float* alo = S.a[s] + TM * KC;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {
+            const int r = warp * 32 + g * 8 + r8, kg = hp * 4 + kq;
+            const float4 a = v[g * 2 + hp];
+            const float4 hi = make_float4(tf32_rn(a.x), tf32_rn(a.y), tf32_rn(a.z), tf32_rn(a.w));
+            const float4 lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
+            const int off = (r >> 3) * (KC / 4 * 32) + kg * 32 + (r & 7) * 4;
+            *reinterpret_cast<float4*>(ahi + off) = hi;
+            *reinterpret_cast<float4*>(alo + off) = lo;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&S.a_full[s]);
+        // segments fully produced so far; flush one behind so the tensor core never waits for us
+        const int produced = (c + 1 == kchunks) ? nseg : (c + 1) / SEG_CHUNKS;
+        while (flushed + 1 < produced) flush(flushed++);
+      }
+      while (flushed < nseg) flush(flushed++);
+      gseg += nseg;
+
+      // ------------------------------- epilogue: acc -> C ------------------------------------------
+      const int N = (int)d->N;
+      const int ncols = min(TN, N - nt * TN);
+      const int64_t ldc = d->ldc;
+      float* C = c_base + d->c_off + (int64_t)nt * TN;
+      const bool accumulate = (d->flags & 1) != 0;
+      float rs = 1.0f;
+      if (d->rs_off >= 0) {
+        const int64_t m = m0 + row;
+        rs = (m < M) ? __ldg(rs_base + d->rs_off + m) : 0.f;
+      }
+      float4* st = reinterpret_cast<float4*>(S.stage[warp]);
+#pragma unroll
+      for (int cb = 0; cb < TN / 32; ++cb) {
+        if (cb * 32 < ncols) {
+          const int rl = lane;  // my row inside the warp's 32 rows
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            st[rl * 8 + (u ^ (rl & 7))] = make_float4(acc[cb * 32 + 4 * u] * rs, acc[cb * 32 + 4 * u + 1] * rs,
+                                                      acc[cb * 32 + 4 * u + 2] * rs, acc[cb * 32 + 4 * u + 3] * rs);
+          __syncwarp();
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const int rr = p * 4 + (lane >> 3), u = lane & 7;
+            const int64_t m = m0 + warp * 32 + rr;
+            const int col = cb * 32 + u * 4;
+            if (m < M && col < ncols) {
+              float4 val = st[rr * 8 + (u ^ (rr & 7))];
+              float4* dst = reinterpret_cast<float4*>(C + m * ldc + col);
+              if (accumulate) {
+                const float4 old = *dst;
+                val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+              }
+              *dst = val;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =========================== weight-chunk loader ===================================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int q = (int)(wi % ntiles_total);
+        const GemmDesc* d = find_desc(descs, ndesc, q);
+        const int nt = q - (int)d->tile0;
+        const int kchunks = (int)d->kchunks;
+        const int ncols = min(TN, (int)d->N - nt * TN);
+        const int nrows = (ncols + 15) & ~15;  // MMA N (multiple of 16); prepared blocks are zero padded
+        const uint32_t bytes = (uint32_t)nrows * KC * sizeof(float);
+        const float* B = b_base + d->b_off + (int64_t)nt * kchunks * BLOCK_FLOATS;
+        for (int c = 0; c < kchunks; ++c, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          if (it >= STAGES) mbar_wait(&S.empty[s], ph ^ 1);
+          mbar_expect_tx(&S.b_full[s], 2 * bytes);
+          bulk_g2s(S.b[s], B + (int64_t)c * BLOCK_FLOATS, bytes, &S.b_full[s]);
+          bulk_g2s(S.b[s] + TN * KC, B + (int64_t)c * BLOCK_FLOATS + TN * KC, bytes, &S.b_full[s]);
+        }
+      }
+    }
+  } else {
+    // =========================== MMA issuer ============================================================
+    if (lane == 0) {
+      constexpr uint32_t SBO = (KC / 4) * 128, LBO = 128;
+      uint32_t it = 0, gseg = 0;
+      for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int q = (int)(wi % ntiles_total);
+        const GemmDesc* d = find_desc(descs, ndesc, q);
+        const int nt = q - (int)d->tile0;
+        const int kchunks = (int)d->kchunks;
+        const int ncols = min(TN, (int)d->N - nt * TN);
+        const int nmma = (ncols + 15) & ~15;
+        const uint32_t idesc = make_idesc(TM, nmma);
+        for (int c0 = 0; c0 < kchunks; c0 += SEG_CHUNKS, ++gseg) {
+          const uint32_t buf = gseg & 1;
+          if (gseg >= 2) mbar_wait(&S.acc_empty[buf], ((gseg >> 1) - 1) & 1);
+          tc_fence_after();
+          const uint32_t d_hh = tmem + buf * 256, d_x = d_hh + 128;
+          uint32_t acc_hh = 0, acc_x = 0;
+          const int c1 = min(kchunks, c0 + SEG_CHUNKS);
+          for (int c = c0; c < c1; ++c, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&S.a_full[s], ph);
+            mbar_wait(&S.b_full[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(S.a[s]), a_lo = a_hi + TM * KC * sizeof(float);
+            const uint32_t b_hi = smem_u32(S.b[s]), b_lo = b_hi + TN * KC * sizeof(float);
+#pragma unroll
+            for (int ks = 0; ks < KC / 8; ++ks) {
+              umma_tf32(d_hh, make_desc(a_hi + ks * 256, LBO, SBO), make_desc(b_hi + ks * 256, LBO, SBO), idesc, acc_hh);
+              acc_hh = 1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < KC / 8; ++ks) {
+              umma_tf32(d_x, make_desc(a_lo + ks * 256, LBO, SBO), make_desc(b_hi + ks * 256, LBO, SBO), idesc, acc_x);
+              acc_x = 1;
+              umma_tf32(d_x, make_desc(a_hi + ks * 256, LBO, SBO), make_desc(b_lo + ks * 256, LBO, SBO), idesc, 1);
+            }
+            umma_commit(&S.empty[s]);
+          }
+          umma_commit(&S.acc_full[buf]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+// prepared layout: for n-tile j, k-chunk c: block (j * kchunks + c) of BLOCK_FLOATS floats = [hi | lo],
+// each [128 rows (n) x 32 (k)] K-major canonical; rows >= N and k >= K are zero.
+__global__ void k_gemm_prepare(const float* __restrict__ B, int64_t ldb, int K, int N, int transposed, float scale,
+                               float* __restrict__ out, int kchunks, int ntiles) {
+  const int64_t total = (int64_t)ntiles * kchunks * TN * KC;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % KC);
+    const int nn = (int)((idx / KC) % TN);
+    const int64_t blk = idx / (KC * TN);
+    const int c = (int)(blk % kchunks), j = (int)(blk / kchunks);
+    const int k = c * KC + kk, n = j * TN + nn;
+    float v = 0.f;
+    if (k < K && n < N) v = (transposed ? B[(int64_t)n * ldb + k] : B[(int64_t)k * ldb + n]) * scale;
+    const float hi = tf32_rn(v), lo = v - hi;
+    float* tile = out + blk * BLOCK_FLOATS;
+    const int off = canon_off(nn, kk, KC / 4);
+    tile[off] = hi;
+    tile[TN * KC + off] = lo;
+  }
+}
+
+}  // namespace
+
+extern "C" int nqb_set_error(const char* msg);
+extern "C" void nqb_count_launch(void);
+
+static int gemm_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+extern "C" int64_t nqb_gemm_prepared_floats(int K, int N) {
+  const int64_t kchunks = (K + KC - 1) / KC, ntiles = (N + TN - 1) / TN;
+  return kchunks * ntiles * BLOCK_FLOATS;
+}
+
+extern "C" int nqb_gemm_prepare(const float* B, int64_t ldb, int K, int N, int transposed, float scale, float* prepared,
+                                nqb_stream_t st) {
+  if (!B || !prepared) return nqb_set_error("nqb_gemm_prepare: null pointer");
+  if (K <= 0 || N <= 0) return nqb_set_error("nqb_gemm_prepare: bad shape");
+  const int kchunks = (K + KC - 1) / KC, ntiles = (N + TN - 1) / TN;
+  const int64_t total = (int64_t)ntiles * kchunks * TN * KC;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  k_gemm_prepare<<<blocks, 256, 0, (cudaStream_t)st>>>(B, ldb, K, N, transposed, scale, prepared, kchunks, ntiles);
+  nqb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const float* a_base,
+                                const float* prepared_base, float* c_base, const float* rowscale_base, int64_t M,
+                                nqb_stream_t st) {
+  if (ndesc <= 0 || ntiles_total <= 0) return nqb_set_error("nqb_gemm_grouped: empty problem list");
+  if (M < 0) return nqb_set_error("nqb_gemm_grouped: negative M");
+  if (M == 0) return 0;
+  if (!descs_dev || !a_base || !prepared_base || !c_base) return nqb_set_error("nqb_gemm_grouped: null pointer");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm3x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+    if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t nwork = ((M + TM - 1) / TM) * (int64_t)ntiles_total;
+  const int grid = (int)(nwork < gemm_sm_count() ? nwork : gemm_sm_count());
+  k_gemm3x<<<grid, 192, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, a_base,
+                                                                 prepared_base, c_base, rowscale_base, M);
+  nqb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
+  return 0;
+}

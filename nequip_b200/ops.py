@@ -387,3 +387,64 @@ def radial_mlp(emb: torch.Tensor, prep: PreparedRadialMLP) -> torch.Tensor:
     if emb.dtype != torch.float32 or emb.dim() != 2 or emb.shape[1] != prep.NUM_BESSEL:
         raise ValueError("radial_mlp: emb must be float32 [E, 8]")
     return _RadialMLPFn.apply(emb.contiguous(), prep)
+
+
+# ---------------------------------------------------------------------------------------
+# grouped fp32-accurate GEMM on the tensor cores (tcgen05 3xTF32) -- nqb_gemm_grouped
+# ---------------------------------------------------------------------------------------
+@dataclass
+class GemmProblem:
+    """C[M, N] (ldc, at c_off) (+)= rowscale[m] * A[M, K] (lda, at a_off) @ B[K, N]."""
+
+    a_off: int
+    lda: int
+    c_off: int
+    ldc: int
+    B: torch.Tensor  # [K, N] (or [N, K] when transposed=True), float32
+    scale: float = 1.0
+    transposed: bool = False
+    accumulate: bool = False
+    rs_off: int = -1  # offset into the rowscale buffer (floats), -1 = none
+
+
+class GroupedGemm:
+    """A fixed list of GEMM problems sharing M, with their weights prepared once (split hi/lo, tiled)."""
+
+    def __init__(self, problems, device):
+        L = _capi.lib()
+        self.problems = list(problems)
+        if not self.problems:
+            raise ValueError("GroupedGemm: empty problem list")
+        rows, blobs, b_off, tile0 = [], [], 0, 0
+        for p in self.problems:
+            K, N = (p.B.shape[1], p.B.shape[0]) if p.transposed else (p.B.shape[0], p.B.shape[1])
+            if any(v % 4 for v in (K, N, p.lda, p.ldc, p.a_off, p.c_off)):
+                raise ValueError("GroupedGemm: K, N, lda, ldc and offsets must be multiples of 4")
+            if p.B.dtype != torch.float32:
+                raise TypeError("GroupedGemm: float32 only")
+            Bc = p.B.detach().to(device).contiguous()
+            nfl = int(L.nqb_gemm_prepared_floats(K, N))
+            prep = torch.empty(nfl, dtype=torch.float32, device=device)
+            _capi.check(L.nqb_gemm_prepare(_ptr(Bc), Bc.shape[1], K, N, int(p.transposed), float(p.scale), _ptr(prep),
+                                           _stream()), "nqb_gemm_prepare")
+            kchunks, ntiles = (K + 31) // 32, (N + 127) // 128
+            rows.append([p.a_off, p.c_off, b_off, p.rs_off, p.lda, p.ldc, K, N, kchunks, ntiles, tile0,
+                         1 if p.accumulate else 0])
+            blobs.append(prep)
+            b_off += nfl
+            tile0 += ntiles
+        self.ntiles_total = tile0
+        self.prepared = torch.cat(blobs)
+        self.descs = torch.tensor(rows, dtype=torch.int64, device=device)
+        self.ndesc = len(rows)
+
+    def run(self, a: torch.Tensor, c: torch.Tensor, M: int, rowscale: Optional[torch.Tensor] = None):
+        _require_cuda(a, c)
+        if a.dtype != torch.float32 or c.dtype != torch.float32:
+            raise TypeError("GroupedGemm.run: float32 only")
+        _capi.check(
+            _capi.lib().nqb_gemm_grouped(_ptr(self.descs), self.ndesc, self.ntiles_total, _ptr(a), _ptr(self.prepared),
+                                         _ptr(c), _ptr(rowscale), int(M), _stream()),
+            "nqb_gemm_grouped",
+        )
+        return c

@@ -1,0 +1,57 @@
+"""GPU parity of the grouped tensor-core GEMM (tcgen05 kind::tf32, 3xTF32 split, segmented fp32
+accumulation) against float64 matmul: the dense algebra of nequip/nn/mlp.py:262-268 and of the
+o3.Linear / self-connection blocks (nequip/nn/interaction_block.py:82-87,129-146)."""
+import pytest
+import torch
+
+from nequip_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("M,K,N", [(1, 4, 4), (127, 8, 8), (300, 64, 64), (1000, 128, 864), (4099, 1728, 128),
+                                   (513, 384, 320), (260, 100, 36)])
+def test_single_problem(M, K, N):
+    g = torch.Generator().manual_seed(M + K + N)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    ref = A.double() @ B.double() * 0.37
+    gg = ops.GroupedGemm([ops.GemmProblem(0, K, 0, N, B, scale=0.37)], "cuda")
+    C = torch.full((M, N), float("nan"), device="cuda")
+    gg.run(A.cuda(), C, M)
+    torch.cuda.synchronize()
+    err = (C.cpu().double() - ref).abs().max().item()
+    assert err <= 1.5e-6 * ref.abs().max().item() + 1e-7, (err, ref.abs().max().item())
+    # transposed weight + accumulate
+    gg2 = ops.GroupedGemm([ops.GemmProblem(0, K, 0, N, B.t().contiguous(), transposed=True, accumulate=True)], "cuda")
+    C2 = torch.ones((M, N), device="cuda")
+    gg2.run(A.cuda(), C2, M)
+    ref2 = A.double() @ B.double() + 1.0
+    err2 = (C2.cpu().double() - ref2).abs().max().item()
+    assert err2 <= 1.5e-6 * ref2.abs().max().item() + 1e-7
+
+
+@pytest.mark.timeout(180)
+def test_grouped_strided_with_rowscale():
+    """Several problems reading column slices of one activation matrix and writing column slices of one
+    output (the ir_mul Linear pattern), one of them row-masked and accumulated (the self-connection pattern)."""
+    g = torch.Generator().manual_seed(5)
+    M, D_in, D_out = 777, 64 + 3 * 32, 128 + 3 * 16
+    X = torch.randn(M, D_in, generator=g)
+    W0, W1 = torch.randn(64, 128, generator=g), torch.randn(32, 16, generator=g)
+    mask = (torch.rand(2, M, generator=g) > 0.5).float()
+    probs = [ops.GemmProblem(0, D_in, 0, D_out, W0)]
+    for i in range(3):
+        probs.append(ops.GemmProblem(64 + 32 * i, D_in, 128 + 16 * i, D_out, W1, scale=0.5))
+    probs.append(ops.GemmProblem(0, D_in, 0, D_out, W0, accumulate=True, rs_off=M))  # masked by mask[1]
+    gg = ops.GroupedGemm(probs, "cuda")
+    out = torch.empty(M, D_out, device="cuda")
+    gg.run(X.cuda(), out, M, rowscale=mask.cuda().contiguous())
+    Xd = X.double()
+    ref = torch.empty(M, D_out, dtype=torch.float64)
+    ref[:, :128] = Xd[:, :64] @ W0.double() + mask[1].double().unsqueeze(1) * (Xd[:, :64] @ W0.double())
+    for i in range(3):
+        ref[:, 128 + 16 * i: 144 + 16 * i] = 0.5 * (Xd[:, 64 + 32 * i: 96 + 32 * i] @ W1.double())
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-6 * ref.abs().max().item(), err
