@@ -142,7 +142,7 @@ int nqb_mlp_bwd(const float* emb, const float* W1s, const float* prep_bwd, const
  * (nequip/nn/mlp.py:262-268), e3nn o3.Linear linear_1/linear_2 and the self-connection
  * FullyConnectedTensorProduct (nequip/nn/interaction_block.py:82-87,129-146) in the ir_mul layout.
  * descs_dev: device array of ndesc records of 12 int64:
- *   {a_off, c_off, b_off, rs_off(-1 = none), lda, ldc, K, N, kchunks=ceil(K/32), ntiles=ceil(N/128),
+ *   {a_off, c_off, b_off, rs_off (row of the [R, rs_ld] row-scale matrix, -1 = none), lda, ldc, K, N, kchunks=ceil(K/32), ntiles=ceil(N/128),
  *    tile0 (prefix sum of ntiles), flags (bit0: accumulate into C)};  offsets in floats from the bases.
  * Requirements: K, N, lda, ldc, a_off, c_off multiples of 4; bases 16-byte aligned.
  * B_p is prepared once (split hi/lo, tiled) with nqb_gemm_prepare into nqb_gemm_prepared_floats(K,N) floats. */
@@ -150,8 +150,8 @@ int64_t nqb_gemm_prepared_floats(int K, int N);
 int nqb_gemm_prepare(const float* B, int64_t ldb, int K, int N, int transposed, float scale, float* prepared,
                      nqb_stream_t st);
 int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const float* a_base,
-                     const float* prepared_base, float* c_base, const float* rowscale_base, int64_t M,
-                     nqb_stream_t st);
+                     const float* prepared_base, float* c_base, const float* rowscale_base, int64_t rs_ld,
+                     int64_t M, nqb_stream_t st);
 
 /* number of kernels the library has launched in this process (bench accounting) */
 int64_t nqb_launch_count(void);

@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 9
+CODEGEN_VERSION = 10
 
 
 # ---------------------------------------------------------------------------
@@ -171,13 +171,15 @@ class GenOptions:
     min_blocks_fwd: int = 4  # __launch_bounds__ minBlocksPerSM (0 = unset); occupancy beats everything else here
     min_blocks_bwd: int = 3
     red_v2: bool = True  # grad_x via red.global.add.v2.f32 (two adjacent floats per atomic)
+    fwd_ring: bool = True  # forward v2: one CTA per node, weight rows streamed through a cp.async.bulk smem ring
+    ring_stages: int = 6
     layout: str = "mul_ir"  # node-feature layout of x / out: "mul_ir" (the reference's, e3nn) or
     #                         "ir_mul" (channel-contiguous: every chunk is [2l+1, mul]; all node-feature
     #                         traffic becomes unit-stride 8-byte accesses; used between our own kernels)
 
     def tag(self) -> str:
         return (f"w{self.nwarp}_a{self.acc_cap}_b{self.acc_cap_bwd}_p{int(self.prefetch)}{int(self.idx_ahead)}"
-                f"_m{self.min_blocks_fwd}{self.min_blocks_bwd}_r{int(self.red_v2)}_{self.layout}")
+                f"_m{self.min_blocks_fwd}{self.min_blocks_bwd}_r{int(self.red_v2)}_{self.layout}_g{int(self.fwd_ring)}{self.ring_stages}")
 
 
 # ---------------------------------------------------------------------------
@@ -418,7 +420,14 @@ class TPGenerator:
         for io in outs:
             n3 = sig.irreps_out[io][1].dim
             em("V " + ", ".join(f"a{io}_{k} = vzero<T>()" for k in range(n3)) + ";")
-        outer = em
+        body = self._fwd_body(paths)
+        self._emit_pipelined_loop(em, paths, body, True)
+        self._emit_fwd_epilogue(em, outs)
+        em.end()
+        em()
+
+    def _fwd_body(self, paths: List[Path]) -> _Emitter:
+        """Per-edge forward math on un-suffixed names (x{i1}_{i}, y{j}, w{p}, accumulators a{io}_{k})."""
         em = _Emitter()
         for (i1, i2), ps in self._blocks(paths):
             l1, l2 = ps[0].l1, ps[0].l2
@@ -457,8 +466,10 @@ class TPGenerator:
                         if f"v{p.idx}_{k}" in started:
                             em(f"a{p.io}_{k} = vfma(w{p.idx}, v{p.idx}_{k}, a{p.io}_{k});")
             em.end()
-        body, em = em, outer
-        self._emit_pipelined_loop(em, paths, body, True)
+        return em
+
+    def _emit_fwd_epilogue(self, em: _Emitter, outs: List[int]):
+        sig = self.sig
         # fold edge sub-groups
         em.block("if (EPW > 1)")
         for io in outs:
@@ -482,6 +493,86 @@ class TPGenerator:
                 for k in range(n3):
                     em(f"vstore<{n3}, {mul}>(op{io} + {k}, a{io}_{k}, ch0);")
         em.end()
+
+    def _emit_fwd2_group(self, em: _Emitter, gid: int, paths: List[Path]):
+        """Forward v2 (float): the node's weight rows arrive through a shared-memory ring filled by
+        cp.async.bulk (one elected lane of warp 0), edge/source ids are staged in shared memory."""
+        sig = self.sig
+        S, W = sig.s_dim, sig.weight_numel
+        outs = sorted({p.io for p in paths})
+        em.block(
+            f"__device__ __forceinline__ void fwd2_g{gid}("
+            "const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w, "
+            "const int64_t* __restrict__ perm, const int64_t* __restrict__ src, "
+            "int64_t n, int64_t beg, int64_t end, int ch0, int sub, int warp, int lane, "
+            "float* ring, uint64_t* full, uint64_t* empty, int64_t* eids, int64_t* srcs, float* __restrict__ out)"
+        )
+        em("typedef float T; typedef VT<float>::V V; constexpr int EPW = VT<float>::EPW; constexpr int LPE = VT<float>::LPE;")
+        for io in outs:
+            n3 = sig.irreps_out[io][1].dim
+            em("V " + ", ".join(f"a{io}_{k} = vzero<T>()" for k in range(n3)) + ";")
+        em("uint32_t base = 0;  // ring iterations completed in earlier passes")
+        em.block("for (int64_t c0 = beg; c0 < end; c0 += F2_CAP)")
+        em("const int cnt = (int)((end - c0 < F2_CAP) ? (end - c0) : F2_CAP);")
+        em("cta_sync();")
+        em.block("for (int i = warp * 32 + lane; i < cnt; i += 32 * NGF)")
+        em("const int64_t e_ = perm ? perm[c0 + i] : (c0 + i);")
+        em("eids[i] = e_; srcs[i] = src[e_];")
+        em.end()
+        em("cta_sync();")
+        em("const int niter = (cnt + EPW - 1) / EPW;")
+        # producer helper
+        em.block("auto issue = [&](int j)")
+        em("const uint32_t gj = base + j, sj = gj % F2_STAGES;")
+        em("if (gj >= F2_STAGES) mbar_wait(&empty[sj], ((gj / F2_STAGES) - 1) & 1);")
+        em("const int r0 = j * EPW;")
+        em("const int rows = (cnt - r0 < EPW) ? (cnt - r0) : EPW;")
+        em(f"mbar_expect_tx(&full[sj], (uint32_t)rows * {W * 4}u);")
+        em(f"for (int r = 0; r < rows; ++r) bulk_g2s(ring + (size_t)(sj * EPW + r) * {W}, w + eids[r0 + r] * {W}, {W * 4}u, &full[sj]);")
+        em.end("};")
+        em.block("if (warp == 0 && lane == 0)")
+        em("for (int j = 0; j < F2_STAGES - 1 && j < niter; ++j) issue(j);")
+        em.end()
+        em.block("for (int it = 0; it < niter; ++it)")
+        em("if (warp == 0 && lane == 0 && it + F2_STAGES - 1 < niter) issue(it + F2_STAGES - 1);")
+        em("const uint32_t gi = base + it, st = gi % F2_STAGES;")
+        em("int slot = it * EPW + sub;")
+        em("const bool valid = slot < cnt;")
+        em("if (!valid) slot = 0;")
+        em("const int64_t e = eids[slot], sn = srcs[slot];")
+        # x and y first (global / L2), then wait for the ring
+        yused, names = self._edge_vars(paths)
+        for j in yused:
+            em(f"const V y{j} = vsplat(__ldg(y + e * {S} + {j}));")
+        for i1 in sorted({p.i1 for p in paths}):
+            mul, ir = sig.irreps_in1[i1]
+            n1 = ir.dim
+            xoff = sig.irreps_in1.offsets()[i1]
+            if self.opts.layout == "ir_mul":
+                al = "true" if (sig.d_in % 2 == 0 and xoff % 2 == 0 and mul % 2 == 0) else "false"
+                em(f"const T* xp{i1} = x + sn * {sig.d_in} + {xoff} + ch0;")
+                for i in range(n1):
+                    em(f"const V x{i1}_{i} = vloadc<{mul}, {al}>(xp{i1} + {i * mul}, ch0);")
+            else:
+                em(f"const T* xp{i1} = x + sn * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
+                for i in range(n1):
+                    em(f"const V x{i1}_{i} = vload<{n1}, {mul}>(xp{i1} + {i}, ch0);")
+        em("mbar_wait(&full[st], (gi / F2_STAGES) & 1);")
+        em(f"const float* wrow = ring + (size_t)(st * EPW + (valid ? sub : 0)) * {W};")
+        for p in paths:
+            al = "true" if (W % 2 == 0 and p.woff % 2 == 0) else "false"
+            em(f"const V w{p.idx} = vloadws<{p.mul}, {al}>(wrow + {p.woff} + ch0, ch0, valid);")
+        em("__syncwarp();")
+        em("if (lane == 0) mbar_arrive(&empty[st]);")
+        body = self._fwd_body(paths)
+        em.block()
+        for ln in body.lines:
+            em(ln)
+        em.end()
+        em.end()  # it loop
+        em("base += niter;")
+        em.end()  # pass loop
+        self._emit_fwd_epilogue(em, outs)
         em.end()
         em()
 
@@ -647,6 +738,13 @@ class TPGenerator:
         em()
         for gid, ps in enumerate(self.fwd_groups):
             self._emit_fwd_group(em, gid, ps)
+        self.use_ring = bool(self.opts.fwd_ring and sig.weight_numel % 4 == 0)
+        if self.use_ring:
+            em(f"constexpr int F2_STAGES = {self.opts.ring_stages};")
+            em("constexpr int F2_CAP = 256;")
+            em("__device__ __forceinline__ void cta_sync() { asm volatile(\"bar.sync 1, %0;\" ::\"n\"(32 * NGF) : \"memory\"); }")
+            for gid, ps in enumerate(self.fwd_groups):
+                self._emit_fwd2_group(em, gid, ps)
         for gid, ps in enumerate(self.bwd_groups):
             self._emit_bwd_group(em, gid, ps)
         mbf = f", {self.opts.min_blocks_fwd}" if self.opts.min_blocks_fwd else ""
@@ -682,6 +780,47 @@ class TPGenerator:
             em.end()
         em.end()
         em()
+        if self.use_ring:
+            minb = max(1, min(16, 512 // (32 * len(self.fwd_groups))))
+            em.block(
+                f"__global__ void __launch_bounds__(32 * NGF, {minb}) tp_fwd2_kernel("
+                "const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w, "
+                "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
+                "const int64_t* __restrict__ src, int64_t N, float* __restrict__ out)"
+            )
+            em("extern __shared__ __align__(16) uint8_t f2_smem[];")
+            em("constexpr int LPE = VT<float>::LPE, CPT = VT<float>::CPT, EPW = VT<float>::EPW;")
+            em(f"constexpr size_t RING_FLOATS = (size_t)F2_STAGES * EPW * {sig.weight_numel};")
+            em("float* ring = reinterpret_cast<float*>(f2_smem);")
+            em("uint64_t* full = reinterpret_cast<uint64_t*>(f2_smem + RING_FLOATS * sizeof(float));")
+            em("uint64_t* empty = full + F2_STAGES;")
+            em("int64_t* eids = reinterpret_cast<int64_t*>(empty + F2_STAGES);")
+            em("int64_t* srcs = eids + F2_CAP;")
+            em("const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
+            em("const int64_t n = blockIdx.x;")
+            em("const int cb = blockIdx.y;")
+            em("const int sub = lane / LPE, cl = lane % LPE;")
+            em("const int ch0 = (cb * LPE + cl) * CPT;")
+            em("const int64_t beg = row_ptr[n], end = row_ptr[n + 1];")
+            em.block("if (threadIdx.x == 0)")
+            em("for (int s_ = 0; s_ < F2_STAGES; ++s_) { mbar_init(&full[s_], 1); mbar_init(&empty[s_], NGF); }")
+            em("fence_barrier_init();")
+            em.end()
+            em("__syncthreads();")
+            em.block("switch (warp)")
+            for gid in range(len(self.fwd_groups)):
+                em(f"case {gid}: fwd2_g{gid}(x, y, w, perm, src, n, beg, end, ch0, sub, warp, lane, ring, full, empty, eids, srcs, out); break;")
+            em("default: break;")
+            em.end()
+            if unwritten:
+                em.block("if (blockIdx.y == 0)")
+                for io in unwritten:
+                    mul, ir = sig.irreps_out[io]
+                    ooff = sig.irreps_out.offsets()[io]
+                    em(f"for (int q = threadIdx.x; q < {mul * ir.dim}; q += blockDim.x) out[n * {sig.d_out} + {ooff} + q] = 0.f;")
+                em.end()
+            em.end()
+            em()
         em.block(
             f"template <typename T, bool WANT_GX> __global__ void __launch_bounds__(32 * NWARP{mbb}) tp_bwd_kernel("
             "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
@@ -724,8 +863,17 @@ class TPGenerator:
         em("if (N <= 0) return 0;")
         em("dim3 block(32 * NWARP);")
         em.block("if (dtype == 0)")
-        em("dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGF * VT<float>::CB);")
-        em("tp_fwd_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, N, (float*)out);")
+        if self.use_ring:
+            lpe_f2, epw_f2, cb_f2 = self.geometry(2)
+            smem = self.opts.ring_stages * epw_f2 * sig.weight_numel * 4 + 2 * self.opts.ring_stages * 8 + 256 * 16
+            em(f"constexpr int F2_SMEM = {smem};")
+            em("static bool attr_set = false;")
+            em("if (!attr_set) { cudaFuncSetAttribute(tp_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM); attr_set = true; }")
+            em("dim3 grid2((unsigned)N, VT<float>::CB), block2(32 * NGF);")
+            em("tp_fwd2_kernel<<<grid2, block2, F2_SMEM, st>>>((const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, N, (float*)out);")
+        else:
+            em("dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGF * VT<float>::CB);")
+            em("tp_fwd_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, N, (float*)out);")
         em.end()
         em.block("else")
         em("dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGF * VT<double>::CB);")

@@ -15,14 +15,16 @@
 // step), so the two cross terms go to their own TMEM accumulator and long reductions are cut into
 // segments of SEG_CHUNKS*32 in K whose partial sums are added in registers (round-to-nearest).
 //
-// Roles per CTA (192 threads, persistent over (M-tile, N-tile) work items, N-tile fastest so that
+// Roles per CTA (320 threads, persistent over (M-tile, N-tile) work items, N-tile fastest so that
 // the CTAs working on one A tile run together and share it in L2):
-//   warps 0-3  stream the A chunk [128 x 32] through registers (coalesced 16-byte loads), split it
-//              hi/lo into the canonical K-major core-matrix layout in shared memory; flush finished
-//              accumulator segments TMEM -> registers; epilogue through a swizzled staging tile so
-//              that the global stores are full 128-byte rows
-//   warp  4    lane 0: cp.async.bulk of the pre-split weight chunk (+ mbarrier complete_tx)
-//   warp  5    lane 0: tcgen05.mma M=128, N<=128, K=8: 4 k-steps x 3 terms per chunk; tcgen05.commit
+//   warps 0-3  producers: stream the A chunk [128 x 32] through registers (coalesced 16-byte loads, one
+//              chunk ahead, across work-item boundaries), split hi/lo into the canonical K-major
+//              core-matrix layout in shared memory
+//   warps 4-7  epilogue: drain finished accumulator segments TMEM -> registers (fp32 adds), then write C
+//              through a swizzled staging tile so that the global stores are full 128-byte rows;
+//              overlaps with the production / MMA of the next work item (TMEM is double buffered)
+//   warp  8    lane 0: cp.async.bulk of the pre-split weight chunk (+ mbarrier complete_tx)
+//   warp  9    lane 0: tcgen05.mma M=128, N<=128, K=8: 4 k-steps x 3 terms per chunk; tcgen05.commit
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -39,7 +41,8 @@ constexpr int SEG_CHUNKS = 10;   // chunks per accumulation segment (40 accumula
 constexpr int BLOCK_FLOATS = 2 * TN * KC;  // one prepared weight block: [hi | lo] x [128 x 32]
 
 struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
-  int64_t a_off, c_off, b_off, rs_off;  // element offsets from the base pointers (rs_off < 0: no row scale)
+  int64_t a_off, c_off, b_off, rs_off;  // element offsets from the base pointers; rs_off = ROW of the
+                                        // [R, rs_ld] row-scale matrix (< 0: no row scale)
   int64_t lda, ldc, K, N;
   int64_t kchunks, ntiles, tile0, flags;  // flags bit0: accumulate into C
 };
@@ -59,9 +62,28 @@ __device__ __forceinline__ const GemmDesc* find_desc(const GemmDesc* d, int nd, 
   return d + i;
 }
 
-__global__ void __launch_bounds__(192, 1)
+struct WorkItem {  // decoded (M-tile, N-tile) work item
+  const GemmDesc* d;
+  int64_t m0;
+  int nt, kchunks, K;
+};
+
+__device__ __forceinline__ bool decode_work(int64_t wi, int64_t nwork, const GemmDesc* descs, int ndesc, int ntiles_total,
+                                            WorkItem& w) {
+  if (wi >= nwork) return false;
+  const int q = (int)(wi % ntiles_total);
+  w.d = find_desc(descs, ndesc, q);
+  w.nt = q - (int)w.d->tile0;
+  w.m0 = (wi / ntiles_total) * TM;
+  w.kchunks = (int)w.d->kchunks;
+  w.K = (int)w.d->K;
+  return true;
+}
+
+__global__ void __launch_bounds__(320, 1)
 k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const float* __restrict__ a_base,
-         const float* __restrict__ b_base, float* __restrict__ c_base, const float* __restrict__ rs_base, int64_t M) {
+         const float* __restrict__ b_base, float* __restrict__ c_base, const float* __restrict__ rs_base, int64_t rs_ld,
+         int64_t M) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -73,103 +95,114 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
     for (int s = 0; s < 2; ++s) { mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 128); }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&S.tmem_base, 512);
+  if (warp == 8) tmem_alloc(&S.tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
 
   if (warp < 4) {
-    // =========================== A producer / segment flush / epilogue ===============================
-    uint32_t it = 0;    // global chunk counter (stage ring)
-    uint32_t gseg = 0;  // global segment counter (accumulator ring)
+    // =========================== A producer: global -> registers (one chunk ahead) -> split -> smem ======
     const int r8 = lane & 7, kq = lane >> 3;
-    const int row = tid;  // accumulator row owned by this thread (TMEM lane)
+    auto load_chunk = [&](const WorkItem& w, int c, float4* v) {
+      const float* A = a_base + w.d->a_off;
+      const int64_t lda = w.d->lda;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int64_t m = w.m0 + warp * 32 + g * 8 + r8;
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {
+          const int k = c * KC + (hp * 4 + kq) * 4;
+          v[g * 2 + hp] = (m < M && k < w.K) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + k))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    WorkItem cur, nxt;
+    int64_t wi = blockIdx.x;
+    bool have = decode_work(wi, nwork, descs, ndesc, ntiles_total, cur);
+    int c = 0;
+    float4 v[8], vn[8];
+    if (have) load_chunk(cur, 0, v);
+    uint32_t it = 0;
+    while (have) {
+      // coordinates of the following chunk (possibly the first chunk of the next work item)
+      bool have_n = true;
+      int cn = c + 1;
+      int64_t win = wi;
+      nxt = cur;
+      if (cn == cur.kchunks) {
+        cn = 0;
+        win = wi + gridDim.x;
+        have_n = decode_work(win, nwork, descs, ndesc, ntiles_total, nxt);
+      }
+      if (have_n) load_chunk(nxt, cn, vn);
+      const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+      if (it >= STAGES) mbar_wait(&S.empty[s], ph ^ 1);
+      float* ahi = S.a[s];
+      float* alo = S.a[s] + TM * KC;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {
+          const int r = warp * 32 + g * 8 + r8, kg = hp * 4 + kq;
+          const float4 a = v[g * 2 + hp];
+          const float4 hi = make_float4(tf32_rn(a.x), tf32_rn(a.y), tf32_rn(a.z), tf32_rn(a.w));
+          const float4 lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
+          const int off = (r >> 3) * (KC / 4 * 32) + kg * 32 + (r & 7) * 4;
+          *reinterpret_cast<float4*>(ahi + off) = hi;
+          *reinterpret_cast<float4*>(alo + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&S.a_full[s]);
+      ++it;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = vn[q];
+      cur = nxt; c = cn; wi = win; have = have_n;
+    }
+  } else if (warp < 8) {
+    // =========================== epilogue: TMEM segments -> registers -> C ============================
+    const int ew = warp - 4;           // TMEM lane quadrant == warp % 4
+    const int row = ew * 32 + lane;    // accumulator row owned by this thread
+    uint32_t gseg = 0;
     float acc[TN];
-    for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-      const int64_t mt = wi / ntiles_total;
-      const int q = (int)(wi % ntiles_total);
-      const GemmDesc* d = find_desc(descs, ndesc, q);
-      const int nt = q - (int)d->tile0;
-      const int K = (int)d->K, kchunks = (int)d->kchunks;
-      const int64_t lda = d->lda;
-      const float* A = a_base + d->a_off;
-      const int64_t m0 = mt * TM;
-      const int nseg = (kchunks + SEG_CHUNKS - 1) / SEG_CHUNKS;
-      int flushed = 0;
+    WorkItem w;
+    for (int64_t wi = blockIdx.x; decode_work(wi, nwork, descs, ndesc, ntiles_total, w); wi += gridDim.x) {
+      const int nseg = (w.kchunks + SEG_CHUNKS - 1) / SEG_CHUNKS;
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[j] = 0.f;
-
-      auto flush = [&](int sidx) {
-        const uint32_t g = gseg + sidx, buf = g & 1;
-        mbar_wait(&S.acc_full[buf], (g >> 1) & 1);
+      for (int sidx = 0; sidx < nseg; ++sidx, ++gseg) {
+        const uint32_t buf = gseg & 1;
+        mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int cb = 0; cb < TN / 16; ++cb) {
           float hh[16], xx[16];
-          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + buf * 256 + cb * 16, hh);
-          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + buf * 256 + 128 + cb * 16, xx);
+          tmem_ld16(tmem + ((uint32_t)(ew * 32) << 16) + buf * 256 + cb * 16, hh);
+          tmem_ld16(tmem + ((uint32_t)(ew * 32) << 16) + buf * 256 + 128 + cb * 16, xx);
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += hh[j] + xx[j];
         }
         tc_fence_before();
         mbar_arrive(&S.acc_empty[buf]);
-      };
-
-      for (int c = 0; c < kchunks; ++c, ++it) {
-        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-        float4 v[8];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int64_t m = m0 + warp * 32 + g * 8 + r8;
-#pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {
-            const int k = c * KC + (hp * 4 + kq) * 4;
-            v[g * 2 + hp] = (m < M && k < K) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + k))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        if (it >= STAGES) mbar_wait(&S.empty[s], ph ^ 1);
-        float* ahi = S.a[s];
-        float* alo = S.a[s] + TM * KC;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-#pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {
-            const int r = warp * 32 + g * 8 + r8, kg = hp * 4 + kq;
-            const float4 a = v[g * 2 + hp];
-            const float4 hi = make_float4(tf32_rn(a.x), tf32_rn(a.y), tf32_rn(a.z), tf32_rn(a.w));
-            const float4 lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
-            const int off = (r >> 3) * (KC / 4 * 32) + kg * 32 + (r & 7) * 4;
-            *reinterpret_cast<float4*>(ahi + off) = hi;
-            *reinterpret_cast<float4*>(alo + off) = lo;
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(&S.a_full[s]);
-        // segments fully produced so far; flush one behind so the tensor core never waits for us
-        const int produced = (c + 1 == kchunks) ? nseg : (c + 1) / SEG_CHUNKS;
-        while (flushed + 1 < produced) flush(flushed++);
       }
-      while (flushed < nseg) flush(flushed++);
-      gseg += nseg;
-
-      // ------------------------------- epilogue: acc -> C ------------------------------------------
+      const GemmDesc* d = w.d;
       const int N = (int)d->N;
-      const int ncols = min(TN, N - nt * TN);
+      const int ncols = min(TN, N - w.nt * TN);
       const int64_t ldc = d->ldc;
-      float* C = c_base + d->c_off + (int64_t)nt * TN;
+      float* C = c_base + d->c_off + (int64_t)w.nt * TN;
       const bool accumulate = (d->flags & 1) != 0;
       float rs = 1.0f;
       if (d->rs_off >= 0) {
-        const int64_t m = m0 + row;
-        rs = (m < M) ? __ldg(rs_base + d->rs_off + m) : 0.f;
+        const int64_t m = w.m0 + row;
+        rs = (m < M) ? __ldg(rs_base + d->rs_off * rs_ld + m) : 0.f;
       }
-      float4* st = reinterpret_cast<float4*>(S.stage[warp]);
+      float4* st = reinterpret_cast<float4*>(S.stage[ew]);
 #pragma unroll
       for (int cb = 0; cb < TN / 32; ++cb) {
         if (cb * 32 < ncols) {
-          const int rl = lane;  // my row inside the warp's 32 rows
+          const int rl = lane;
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             st[rl * 8 + (u ^ (rl & 7))] = make_float4(acc[cb * 32 + 4 * u] * rs, acc[cb * 32 + 4 * u + 1] * rs,
@@ -178,7 +211,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
             const int rr = p * 4 + (lane >> 3), u = lane & 7;
-            const int64_t m = m0 + warp * 32 + rr;
+            const int64_t m = w.m0 + ew * 32 + rr;
             const int col = cb * 32 + u * 4;
             if (m < M && col < ncols) {
               float4 val = st[rr * 8 + (u ^ (rr & 7))];
@@ -194,20 +227,17 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // =========================== weight-chunk loader ===================================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-        const int q = (int)(wi % ntiles_total);
-        const GemmDesc* d = find_desc(descs, ndesc, q);
-        const int nt = q - (int)d->tile0;
-        const int kchunks = (int)d->kchunks;
-        const int ncols = min(TN, (int)d->N - nt * TN);
+      WorkItem w;
+      for (int64_t wi = blockIdx.x; decode_work(wi, nwork, descs, ndesc, ntiles_total, w); wi += gridDim.x) {
+        const int ncols = min(TN, (int)w.d->N - w.nt * TN);
         const int nrows = (ncols + 15) & ~15;  // MMA N (multiple of 16); prepared blocks are zero padded
         const uint32_t bytes = (uint32_t)nrows * KC * sizeof(float);
-        const float* B = b_base + d->b_off + (int64_t)nt * kchunks * BLOCK_FLOATS;
-        for (int c = 0; c < kchunks; ++c, ++it) {
+        const float* B = b_base + w.d->b_off + (int64_t)w.nt * w.kchunks * BLOCK_FLOATS;
+        for (int c = 0; c < w.kchunks; ++c, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           if (it >= STAGES) mbar_wait(&S.empty[s], ph ^ 1);
           mbar_expect_tx(&S.b_full[s], 2 * bytes);
@@ -221,21 +251,18 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
     if (lane == 0) {
       constexpr uint32_t SBO = (KC / 4) * 128, LBO = 128;
       uint32_t it = 0, gseg = 0;
-      for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-        const int q = (int)(wi % ntiles_total);
-        const GemmDesc* d = find_desc(descs, ndesc, q);
-        const int nt = q - (int)d->tile0;
-        const int kchunks = (int)d->kchunks;
-        const int ncols = min(TN, (int)d->N - nt * TN);
+      WorkItem w;
+      for (int64_t wi = blockIdx.x; decode_work(wi, nwork, descs, ndesc, ntiles_total, w); wi += gridDim.x) {
+        const int ncols = min(TN, (int)w.d->N - w.nt * TN);
         const int nmma = (ncols + 15) & ~15;
         const uint32_t idesc = make_idesc(TM, nmma);
-        for (int c0 = 0; c0 < kchunks; c0 += SEG_CHUNKS, ++gseg) {
+        for (int c0 = 0; c0 < w.kchunks; c0 += SEG_CHUNKS, ++gseg) {
           const uint32_t buf = gseg & 1;
           if (gseg >= 2) mbar_wait(&S.acc_empty[buf], ((gseg >> 1) - 1) & 1);
           tc_fence_after();
           const uint32_t d_hh = tmem + buf * 256, d_x = d_hh + 128;
           uint32_t acc_hh = 0, acc_x = 0;
-          const int c1 = min(kchunks, c0 + SEG_CHUNKS);
+          const int c1 = min(w.kchunks, c0 + SEG_CHUNKS);
           for (int c = c0; c < c1; ++c, ++it) {
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(&S.a_full[s], ph);
@@ -263,7 +290,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 // prepared layout: for n-tile j, k-chunk c: block (j * kchunks + c) of BLOCK_FLOATS floats = [hi | lo],
@@ -324,8 +351,8 @@ extern "C" int nqb_gemm_prepare(const float* B, int64_t ldb, int K, int N, int t
 }
 
 extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const float* a_base,
-                                const float* prepared_base, float* c_base, const float* rowscale_base, int64_t M,
-                                nqb_stream_t st) {
+                                const float* prepared_base, float* c_base, const float* rowscale_base, int64_t rs_ld,
+                                int64_t M, nqb_stream_t st) {
   if (ndesc <= 0 || ntiles_total <= 0) return nqb_set_error("nqb_gemm_grouped: empty problem list");
   if (M < 0) return nqb_set_error("nqb_gemm_grouped: negative M");
   if (M == 0) return 0;
@@ -338,8 +365,8 @@ extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_tot
   }
   const int64_t nwork = ((M + TM - 1) / TM) * (int64_t)ntiles_total;
   const int grid = (int)(nwork < gemm_sm_count() ? nwork : gemm_sm_count());
-  k_gemm3x<<<grid, 192, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, a_base,
-                                                                 prepared_base, c_base, rowscale_base, M);
+  k_gemm3x<<<grid, 320, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, a_base,
+                                                                 prepared_base, c_base, rowscale_base, rs_ld, M);
   nqb_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));

@@ -164,6 +164,49 @@ template <int MUL, bool AL2> __device__ __forceinline__ void vstorew(double* __r
   if (full || ch0 < MUL) p[0] = v;
 }
 
+// ---- shared-memory weight ring (forward v2): mbarrier + cp.async.bulk ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// weights of the channel pair from the shared-memory ring
+template <int MUL, bool AL2> __device__ __forceinline__ float2 vloadws(const float* p, int ch0, bool valid) {
+  constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;
+  float2 r = make_float2(0.f, 0.f);
+  if (valid) {
+    if (full && AL2) {
+      r = *reinterpret_cast<const float2*>(p);
+    } else {
+      if (full || ch0 < MUL) r.x = p[0];
+      if (full || ch0 + 1 < MUL) r.y = p[1];
+    }
+  }
+  return r;
+}
+
 // ---- cross-lane -----------------------------------------------------------------------
 // sum the partial accumulators of the EPW edge sub-groups (lanes l, l+LPE, l+2LPE, ...)
 template <int LPE> __device__ __forceinline__ float2 vfold(float2 a) {

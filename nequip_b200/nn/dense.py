@@ -1,0 +1,173 @@
+"""Dense blocks of the interaction layer on the tensor cores (inference: frozen weights, float32,
+channel-contiguous ``ir_mul`` node layout).
+
+Each block is ONE launch of the grouped 3xTF32 GEMM (``nequip_b200/csrc/nqb_gemm.cu``) per
+direction; the weights are prepared (scaled, split hi/lo, tiled) once.  Reference ops:
+
+* ``RadialMLPGemm``      ScalarMLPFunction, depth 1            nequip/nn/mlp.py:80-195, 262-268
+* ``IrrepsLinearGemm``   e3nn o3.Linear (linear_1, linear_2)   nequip/nn/interaction_block.py:82-87,129-138
+* ``SelfConnectionGemm`` e3nn FullyConnectedTensorProduct(x, node_attrs) with node_attrs =
+                         type_embed[atom_types]                nequip/nn/interaction_block.py:140-146,175
+
+In ir_mul every (chunk pair, irrep component) is a strided GEMM over the atoms:
+``out[:, oo + i*mo : oo + (i+1)*mo] (+)= x[:, io + i*mi : io + (i+1)*mi] @ W``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from .. import ops
+from ..irreps import Irreps
+
+
+def _aligned(*vals) -> bool:
+    return all(v % 4 == 0 for v in vals)
+
+
+# ---------------------------------------------------------------------------------------
+class _GemmLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fwd: ops.GroupedGemm, bwd: ops.GroupedGemm, d_out: int, zero_out: bool, d_in: int, zero_in: bool,
+                rowscale, out_init):
+        M = x.shape[0]
+        if out_init is not None:
+            out = out_init  # accumulate into an existing tensor (self-connection added onto linear_2's output)
+        else:
+            out = (torch.zeros if zero_out else torch.empty)((M, d_out), dtype=x.dtype, device=x.device)
+        fwd.run(x, out, M, rowscale)
+        ctx.bwd, ctx.d_in, ctx.zero_in, ctx.rowscale = bwd, d_in, zero_in, rowscale
+        ctx.has_init = out_init is not None
+        if out_init is not None:
+            ctx.mark_dirty(out_init)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        gout = gout.contiguous()
+        M = gout.shape[0]
+        gx = (torch.zeros if ctx.zero_in else torch.empty)((M, ctx.d_in), dtype=gout.dtype, device=gout.device)
+        ctx.bwd.run(gout, gx, M, ctx.rowscale)
+        return gx, None, None, None, None, None, None, None, (gout if ctx.has_init else None)
+
+
+class IrrepsLinearGemm:
+    """``o3.Linear`` in ir_mul layout from a ``nequip_b200.nn.model.Linear`` module's weights."""
+
+    def __init__(self, lin, device, extra_scale: float = 1.0):
+        fin, fout = lin.irreps_in, lin.irreps_out
+        in_off, out_off = fin.offsets(), fout.offsets()
+        self.d_in, self.d_out = fin.dim, fout.dim
+        fwd: List[ops.GemmProblem] = []
+        bwd: List[ops.GemmProblem] = []
+        out_written, in_written = set(), set()
+        for (i, o, off, pw) in lin.instr:
+            mi, ir = fin[i]
+            mo = fout[o][0]
+            W = lin.weight.detach()[off: off + mi * mo].view(mi, mo)
+            for c in range(ir.dim):
+                a_off, c_off = in_off[i] + c * mi, out_off[o] + c * mo
+                fwd.append(ops.GemmProblem(a_off, self.d_in, c_off, self.d_out, W, scale=pw * extra_scale,
+                                           accumulate=(o, c) in out_written))
+                out_written.add((o, c))
+                bwd.append(ops.GemmProblem(c_off, self.d_out, a_off, self.d_in, W, scale=pw * extra_scale, transposed=True,
+                                           accumulate=(i, c) in in_written))
+                in_written.add((i, c))
+        self.zero_out = any((o, c) not in out_written for o, (mo, ir) in enumerate(fout) for c in range(ir.dim))
+        self.zero_in = any((i, c) not in in_written for i, (mi, ir) in enumerate(fin) for c in range(ir.dim))
+        self.fwd = ops.GroupedGemm(fwd, device)
+        self.bwd = ops.GroupedGemm(bwd, device)
+
+    @staticmethod
+    def supported(lin) -> bool:
+        muls = [m for m, _ in lin.irreps_in] + [m for m, _ in lin.irreps_out]
+        return lin.layout == "ir_mul" and all(m % 4 == 0 for m in muls) and lin.weight.dtype == torch.float32
+
+    def __call__(self, x):
+        return _GemmLinearFn.apply(x.contiguous(), self.fwd, self.bwd, self.d_out, self.zero_out, self.d_in, self.zero_in,
+                                   None, None)
+
+
+class SelfConnectionGemm:
+    """FCTP(x, type_embed[types]) as per-type effective-weight GEMMs with a one-hot row scale; the result
+    is ACCUMULATED onto ``base`` (the linear_2 output), i.e. ``x = linear_2(x) + sc`` in one pass."""
+
+    def __init__(self, sc, type_table: torch.Tensor, device):
+        fin, fout = sc.irreps_in, sc.irreps_out
+        in_off, out_off = fin.offsets(), fout.offsets()
+        self.d_in, self.d_out = fin.dim, fout.dim
+        self.T = type_table.shape[0]
+        fwd: List[ops.GemmProblem] = []
+        bwd: List[ops.GemmProblem] = []
+        in_written = set()
+        tt = type_table.detach()
+        for (i, o, off, pw) in sc.instr:
+            mi, ir = fin[i]
+            mo = fout[o][0]
+            W = sc.weight.detach()[off: off + mi * sc.num_attr * mo].view(mi, sc.num_attr, mo)
+            weff = torch.einsum("uvw,tv->tuw", W, tt)  # [T, mi, mo]
+            for t in range(self.T):
+                for c in range(ir.dim):
+                    a_off, c_off = in_off[i] + c * mi, out_off[o] + c * mo
+                    # row scale = row t of one-hot^T [T, M]
+                    fwd.append(ops.GemmProblem(a_off, self.d_in, c_off, self.d_out, weff[t].contiguous(), scale=pw,
+                                               accumulate=True, rs_off=t))
+                    bwd.append(ops.GemmProblem(c_off, self.d_out, a_off, self.d_in, weff[t].contiguous(), scale=pw,
+                                               transposed=True, accumulate=(i, c) in in_written, rs_off=t))
+                    in_written.add((i, c))
+        self.zero_in = any((i, c) not in in_written for i, (mi, ir) in enumerate(fin) for c in range(ir.dim))
+        self.fwd = ops.GroupedGemm(fwd, device)
+        self.bwd = ops.GroupedGemm(bwd, device)
+
+    @staticmethod
+    def supported(sc) -> bool:
+        muls = [m for m, _ in sc.irreps_in] + [m for m, _ in sc.irreps_out]
+        return sc.layout == "ir_mul" and all(m % 4 == 0 for m in muls) and sc.weight.dtype == torch.float32
+
+    def __call__(self, x, types, base):
+        onehot_t = torch.nn.functional.one_hot(types, self.T).to(x.dtype).t().contiguous()  # [T, M]
+        return _GemmLinearFn.apply(x.contiguous(), self.fwd, self.bwd, self.d_out, False, self.d_in, self.zero_in,
+                                   onehot_t, base)
+
+
+# ---------------------------------------------------------------------------------------
+class _RadialMLPGemmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, w1s, fwd: ops.GroupedGemm, bwd: ops.GroupedGemm, W: int):
+        E = emb.shape[0]
+        pre = torch.mm(emb, w1s)  # K = 8: not worth a tensor-core pass
+        h = torch.nn.functional.silu(pre)
+        out = torch.empty((E, W), dtype=emb.dtype, device=emb.device)
+        fwd.run(h, out, E)
+        ctx.bwd, ctx.w1s = bwd, w1s
+        ctx.save_for_backward(pre)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gw):
+        (pre,) = ctx.saved_tensors
+        E = pre.shape[0]
+        gh = torch.empty_like(pre)
+        ctx.bwd.run(gw.contiguous(), gh, E)
+        gpre = torch.ops.aten.silu_backward(gh, pre)
+        return torch.mm(gpre, ctx.w1s.t()), None, None, None, None
+
+
+class RadialMLPGemm:
+    def __init__(self, lin1, lin2, device):
+        self.w1s = (lin1.weight.detach() * lin1.alpha).contiguous()
+        hid, W = lin2.weight.shape
+        self.W = W
+        a2 = float(lin2.alpha)
+        self.fwd = ops.GroupedGemm([ops.GemmProblem(0, hid, 0, W, lin2.weight.detach(), scale=a2)], device)
+        self.bwd = ops.GroupedGemm([ops.GemmProblem(0, W, 0, hid, lin2.weight.detach(), scale=a2, transposed=True)], device)
+
+    @staticmethod
+    def supported(lin1, lin2, dtype) -> bool:
+        return dtype == torch.float32 and lin2.weight.shape[0] % 4 == 0 and lin2.weight.shape[1] % 4 == 0
+
+    def __call__(self, emb):
+        return _RadialMLPGemmFn.apply(emb.contiguous(), self.w1s, self.fwd, self.bwd, self.W)

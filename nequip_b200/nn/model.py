@@ -304,7 +304,9 @@ class InteractionBlock(torch.nn.Module):
         self.linear_2 = Linear(irreps_mid.simplify(), fout, layout)
         self.sc = SelfConnection(fin, num_node_attrs, fout, layout) if use_sc else None
         self.use_tensor_core_mlp = True
+        self.use_tensor_cores = True
         self._prep_mlp = None
+        self._tc_cache = None
 
     def _edge_weights(self, edge_embedding):
         """Radial MLP.  Depth-1 / width-128 float32 networks whose weights are frozen (inference) run
@@ -333,6 +335,21 @@ class InteractionBlock(torch.nn.Module):
             x = x[:n_own]
             node_attrs = node_attrs[:n_own]
             types = None if types is None else types[:n_own]
+        tc = self._tensor_core_blocks(x, types, type_table)
+        if tc is not None:
+            # inference fast path: every dense block is one grouped 3xTF32 tcgen05 GEMM launch
+            x_in = x
+            x = tc["lin1"](x)  # 1/sqrt(avg_num_neighbors) folded into the prepared weights
+            if halo is not None and not self.is_first_layer:
+                x = halo(x)
+            w = tc["mlp"](edge_embedding) if tc["mlp"] is not None else self._edge_weights(edge_embedding)
+            x = self.tp_scatter(x=x, edge_attr=edge_attrs, edge_weight=w, edge_dst=edge_index[0], edge_src=edge_index[1])
+            if n_own is not None:
+                x = x[:n_own]
+            x = tc["lin2"](x)
+            if tc["sc"] is not None:
+                x = tc["sc"](x_in, types, x)  # accumulates the self-connection onto linear_2's output
+            return x
         sc = self.sc(x, node_attrs, types, type_table) if self.sc is not None else None
         x = self.linear_1(x)
         x = x * self.norm_const
@@ -346,6 +363,41 @@ class InteractionBlock(torch.nn.Module):
         if sc is not None:
             x = x + sc
         return x
+
+    def _tensor_core_blocks(self, x, types, type_table):
+        """Lazily prepared tensor-core versions of linear_1 / radial MLP / linear_2 / self-connection
+        (nequip_b200/nn/dense.py); None when not applicable (training, float64, mul_ir, odd multiplicities)."""
+        from . import dense
+
+        if not (self.use_tensor_cores and x.is_cuda and x.dtype == torch.float32 and self.layout == "ir_mul"):
+            return None
+        if any(p.requires_grad for p in self.parameters()) or (type_table is not None and type_table.requires_grad):
+            return None
+        if self.sc is not None and (types is None or type_table is None):
+            return None
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (
+            (type_table.data_ptr(), type_table._version) if type_table is not None else ())
+        if self._tc_cache is not None and self._tc_cache[0] == key:
+            return self._tc_cache[1]
+        ok = dense.IrrepsLinearGemm.supported(self.linear_1) and dense.IrrepsLinearGemm.supported(self.linear_2)
+        if self.sc is not None:
+            ok = ok and dense.SelfConnectionGemm.supported(self.sc)
+        if not ok:
+            self._tc_cache = (key, None)
+            return None
+        dev = x.device
+        lins = [m for m in self.edge_mlp.mlp if isinstance(m, ScalarLinearLayer)]
+        mlp = None
+        if len(lins) == 2 and dense.RadialMLPGemm.supported(lins[0], lins[1], x.dtype):
+            mlp = dense.RadialMLPGemm(lins[0], lins[1], dev)
+        blocks = dict(
+            lin1=dense.IrrepsLinearGemm(self.linear_1, dev, extra_scale=float(self.norm_const)),
+            lin2=dense.IrrepsLinearGemm(self.linear_2, dev),
+            sc=dense.SelfConnectionGemm(self.sc, type_table, dev) if self.sc is not None else None,
+            mlp=mlp,
+        )
+        self._tc_cache = (key, blocks)
+        return blocks
 
 
 class ConvNetLayer(torch.nn.Module):

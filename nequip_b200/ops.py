@@ -404,7 +404,7 @@ class GemmProblem:
     scale: float = 1.0
     transposed: bool = False
     accumulate: bool = False
-    rs_off: int = -1  # offset into the rowscale buffer (floats), -1 = none
+    rs_off: int = -1  # row of the [R, M] row-scale matrix, -1 = none
 
 
 class GroupedGemm:
@@ -444,7 +444,7 @@ class GroupedGemm:
             raise TypeError("GroupedGemm.run: float32 only")
         _capi.check(
             _capi.lib().nqb_gemm_grouped(_ptr(self.descs), self.ndesc, self.ntiles_total, _ptr(a), _ptr(self.prepared),
-                                         _ptr(c), _ptr(rowscale), int(M), _stream()),
+                                         _ptr(c), _ptr(rowscale), (int(rowscale.shape[-1]) if rowscale is not None else 0), int(M), _stream()),
             "nqb_gemm_grouped",
         )
         return c

@@ -44,7 +44,7 @@ def test_grouped_strided_with_rowscale():
     probs = [ops.GemmProblem(0, D_in, 0, D_out, W0)]
     for i in range(3):
         probs.append(ops.GemmProblem(64 + 32 * i, D_in, 128 + 16 * i, D_out, W1, scale=0.5))
-    probs.append(ops.GemmProblem(0, D_in, 0, D_out, W0, accumulate=True, rs_off=M))  # masked by mask[1]
+    probs.append(ops.GemmProblem(0, D_in, 0, D_out, W0, accumulate=True, rs_off=1))  # masked by mask[1]
     gg = ops.GroupedGemm(probs, "cuda")
     out = torch.empty(M, D_out, device="cuda")
     gg.run(X.cuda(), out, M, rowscale=mask.cuda().contiguous())

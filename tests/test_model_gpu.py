@@ -108,7 +108,8 @@ def test_energy_forces_inference_path_tensor_core_mlp(name):
     n0 = _capi.launch_count()
     out = model(D.to_device(sysd, "cuda"))
     torch.cuda.synchronize()
-    assert all(l.conv._prep_mlp is not None for l in model.layers), "tensor-core MLP path not taken"
+    assert all(l.conv._tc_cache is not None and l.conv._tc_cache[1] is not None for l in model.layers), \
+        "tensor-core dense path not taken"
     assert _capi.launch_count() - n0 >= 4 * len(model.layers)
     e_ref, ea_ref, f_ref = omodel.energy_and_forces(model.state_dict(), model.config, sysd, torch.float32)
     e, f = out["total_energy"].cpu(), out["forces"].cpu()

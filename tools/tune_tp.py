@@ -14,15 +14,11 @@ from nequip_b200.codegen import GenOptions  # noqa: E402
 from nequip_b200.known_signatures import nequip_layer_signatures  # noqa: E402
 
 VARIANTS = {
-    "default": GenOptions(),
-    "irmul": GenOptions(layout="ir_mul"),
-    "irmul_nopf": GenOptions(layout="ir_mul", prefetch=False, idx_ahead=False),
-    "irmul_nopf_mb0": GenOptions(layout="ir_mul", prefetch=False, idx_ahead=False, min_blocks_fwd=0, min_blocks_bwd=0),
-    "irmul_pf_mb0": GenOptions(layout="ir_mul", min_blocks_fwd=0, min_blocks_bwd=0),
-    "irmul_mb5": GenOptions(layout="ir_mul", min_blocks_fwd=5, min_blocks_bwd=4),
-    "irmul_nopf_mb5": GenOptions(layout="ir_mul", prefetch=False, idx_ahead=False, min_blocks_fwd=5, min_blocks_bwd=4),
-    "irmul_a16_mb6": GenOptions(layout="ir_mul", acc_cap=16, acc_cap_bwd=12, min_blocks_fwd=6, min_blocks_bwd=4),
-    "irmul_nopf_a16_mb6": GenOptions(layout="ir_mul", prefetch=False, idx_ahead=False, acc_cap=16, acc_cap_bwd=12, min_blocks_fwd=6, min_blocks_bwd=4),
+    "irmul_ring6": GenOptions(layout="ir_mul"),
+    "irmul_noring": GenOptions(layout="ir_mul", fwd_ring=False),
+    "irmul_ring4": GenOptions(layout="ir_mul", ring_stages=4),
+    "irmul_ring8": GenOptions(layout="ir_mul", ring_stages=8),
+    "mulir_ring6": GenOptions(layout="mul_ir"),
 }
 _OLD = {
     "nopf": GenOptions(prefetch=False, idx_ahead=False),
