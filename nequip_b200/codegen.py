@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 10
+CODEGEN_VERSION = 12
 
 
 # ---------------------------------------------------------------------------
@@ -172,14 +172,15 @@ class GenOptions:
     min_blocks_bwd: int = 3
     red_v2: bool = True  # grad_x via red.global.add.v2.f32 (two adjacent floats per atomic)
     fwd_ring: bool = True  # forward v2: one CTA per node, weight rows streamed through a cp.async.bulk smem ring
-    ring_stages: int = 6
+    ring_stages: int = 4
+    bwd_ring: bool = True  # backward v2 (same weight ring)
     layout: str = "mul_ir"  # node-feature layout of x / out: "mul_ir" (the reference's, e3nn) or
     #                         "ir_mul" (channel-contiguous: every chunk is [2l+1, mul]; all node-feature
     #                         traffic becomes unit-stride 8-byte accesses; used between our own kernels)
 
     def tag(self) -> str:
         return (f"w{self.nwarp}_a{self.acc_cap}_b{self.acc_cap_bwd}_p{int(self.prefetch)}{int(self.idx_ahead)}"
-                f"_m{self.min_blocks_fwd}{self.min_blocks_bwd}_r{int(self.red_v2)}_{self.layout}_g{int(self.fwd_ring)}{self.ring_stages}")
+                f"_m{self.min_blocks_fwd}{self.min_blocks_bwd}_r{int(self.red_v2)}_{self.layout}_g{int(self.fwd_ring)}{self.ring_stages}{int(self.bwd_ring)}")
 
 
 # ---------------------------------------------------------------------------
@@ -578,9 +579,6 @@ class TPGenerator:
 
     # -- backward ---------------------------------------------------------------------
     def _emit_bwd_group(self, em: _Emitter, gid: int, paths: List[Path]):
-        sig = self.sig
-        S = sig.s_dim
-        outs = sorted({p.io for p in paths})
         em.block(
             f"template <typename T, bool WANT_GX> __device__ __forceinline__ void bwd_g{gid}("
             "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
@@ -589,6 +587,16 @@ class TPGenerator:
             "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw)"
         )
         em("typedef typename VT<T>::V V; constexpr int EPW = VT<T>::EPW; constexpr int LPE = VT<T>::LPE;")
+        self._emit_bwd_prologue(em, paths)
+        body = self._bwd_body(paths)
+        self._emit_pipelined_loop(em, paths, body, False)
+        em.end()
+        em()
+
+    def _emit_bwd_prologue(self, em: _Emitter, paths: List[Path]):
+        """grad_out rows of this node (resident in registers for the whole edge loop) + reduce constants."""
+        sig = self.sig
+        outs = sorted({p.io for p in paths})
         for io in outs:
             mul, ir = sig.irreps_out[io]
             n3 = ir.dim
@@ -606,7 +614,12 @@ class TPGenerator:
         yused, _ = self._edge_vars(paths)
         Pq = _pow2ceil(yused[-1] + 1 - yused[0])
         em(f"const int qbase = er_base<LPE, {Pq}>(cl); const bool qlead = er_leader<LPE, {Pq}>(cl);")
-        outer = em
+
+    def _bwd_body(self, paths: List[Path]) -> _Emitter:
+        """Per-edge backward math on un-suffixed names (inputs x, y, w, valid, e, sn; resident g)."""
+        sig = self.sig
+        S = sig.s_dim
+        yused, _ = self._edge_vars(paths)
         em = _Emitter()
         em("V " + ", ".join(f"q{j} = vzero<T>()" for j in yused) + ";")
         for i1 in sorted({p.i1 for p in paths}):
@@ -703,8 +716,81 @@ class TPGenerator:
         em("#pragma unroll")
         em(f"for (int j = 0; j < QC; ++j) if (qbase + j < {y1 - y0}) atomicAdd(gy + e * {S} + {y0} + qbase + j, qv[j]);")
         em.end()
-        body, em = em, outer
-        self._emit_pipelined_loop(em, paths, body, False)
+        return em
+
+    def _emit_bwd2_group(self, em: _Emitter, gid: int, paths: List[Path]):
+        """Backward v2 (float): same shared-memory weight ring as forward v2."""
+        sig = self.sig
+        S, W = sig.s_dim, sig.weight_numel
+        em.block(
+            f"template <bool WANT_GX> __device__ __forceinline__ void bwd2_g{gid}("
+            "const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w, "
+            "const int64_t* __restrict__ perm, const int64_t* __restrict__ src, const float* __restrict__ gout, "
+            "int64_t n, int64_t beg, int64_t end, int ch0, int sub, int cl, int warp, int lane, "
+            "float* ring, uint64_t* full, uint64_t* empty, int64_t* eids, int64_t* srcs, "
+            "float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gw)"
+        )
+        em("typedef float T; typedef VT<float>::V V; constexpr int EPW = VT<float>::EPW; constexpr int LPE = VT<float>::LPE;")
+        self._emit_bwd_prologue(em, paths)
+        em("uint32_t base = 0;")
+        em.block("for (int64_t c0 = beg; c0 < end; c0 += B2_CAP)")
+        em("const int cnt = (int)((end - c0 < B2_CAP) ? (end - c0) : B2_CAP);")
+        em("cta_sync_b();")
+        em.block("for (int i = warp * 32 + lane; i < cnt; i += 32 * NGB)")
+        em("const int64_t e_ = perm ? perm[c0 + i] : (c0 + i);")
+        em("eids[i] = e_; srcs[i] = src[e_];")
+        em.end()
+        em("cta_sync_b();")
+        em("const int niter = (cnt + EPW - 1) / EPW;")
+        em.block("auto issue = [&](int j)")
+        em("const uint32_t gj = base + j, sj = gj % B2_STAGES;")
+        em("if (gj >= B2_STAGES) mbar_wait(&empty[sj], ((gj / B2_STAGES) - 1) & 1);")
+        em("const int r0 = j * EPW;")
+        em("const int rows = (cnt - r0 < EPW) ? (cnt - r0) : EPW;")
+        em(f"mbar_expect_tx(&full[sj], (uint32_t)rows * {W * 4}u);")
+        em(f"for (int r = 0; r < rows; ++r) bulk_g2s(ring + (size_t)(sj * EPW + r) * {W}, w + eids[r0 + r] * {W}, {W * 4}u, &full[sj]);")
+        em.end("};")
+        em.block("if (warp == 0 && lane == 0)")
+        em("for (int j = 0; j < B2_STAGES - 1 && j < niter; ++j) issue(j);")
+        em.end()
+        em.block("for (int it = 0; it < niter; ++it)")
+        em("if (warp == 0 && lane == 0 && it + B2_STAGES - 1 < niter) issue(it + B2_STAGES - 1);")
+        em("const uint32_t gi = base + it, st = gi % B2_STAGES;")
+        em("int slot = it * EPW + sub;")
+        em("const bool valid = slot < cnt;")
+        em("if (!valid) slot = 0;")
+        em("const int64_t e = eids[slot], sn = srcs[slot];")
+        yused, names = self._edge_vars(paths)
+        for j in yused:
+            em(f"const V y{j} = vsplat(__ldg(y + e * {S} + {j}));")
+        for i1 in sorted({p.i1 for p in paths}):
+            mul, ir = sig.irreps_in1[i1]
+            n1 = ir.dim
+            xoff = sig.irreps_in1.offsets()[i1]
+            if self.opts.layout == "ir_mul":
+                al = "true" if (sig.d_in % 2 == 0 and xoff % 2 == 0 and mul % 2 == 0) else "false"
+                em(f"const T* xp{i1} = x + sn * {sig.d_in} + {xoff} + ch0;")
+                for i in range(n1):
+                    em(f"const V x{i1}_{i} = vloadc<{mul}, {al}>(xp{i1} + {i * mul}, ch0);")
+            else:
+                em(f"const T* xp{i1} = x + sn * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
+                for i in range(n1):
+                    em(f"const V x{i1}_{i} = vload<{n1}, {mul}>(xp{i1} + {i}, ch0);")
+        em("mbar_wait(&full[st], (gi / B2_STAGES) & 1);")
+        em(f"const float* wrow = ring + (size_t)(st * EPW + (valid ? sub : 0)) * {W};")
+        for p in paths:
+            al = "true" if (W % 2 == 0 and p.woff % 2 == 0) else "false"
+            em(f"const V w{p.idx} = vloadws<{p.mul}, {al}>(wrow + {p.woff} + ch0, ch0, true);")
+        em("__syncwarp();")
+        em("if (lane == 0) mbar_arrive(&empty[st]);")
+        body = self._bwd_body(paths)
+        em.block()
+        for ln in body.lines:
+            em(ln)
+        em.end()
+        em.end()  # it loop
+        em("base += niter;")
+        em.end()  # pass loop
         em.end()
         em()
 
@@ -738,7 +824,9 @@ class TPGenerator:
         em()
         for gid, ps in enumerate(self.fwd_groups):
             self._emit_fwd_group(em, gid, ps)
-        self.use_ring = bool(self.opts.fwd_ring and sig.weight_numel % 4 == 0)
+        # the ring pays off when several warps (path groups) share one node's weight rows; single-group
+        # signatures (3-4 paths: first/last layer) keep the register-resident v1 kernel (measured)
+        self.use_ring = bool(self.opts.fwd_ring and sig.weight_numel % 4 == 0 and len(self.fwd_groups) >= 2)
         if self.use_ring:
             em(f"constexpr int F2_STAGES = {self.opts.ring_stages};")
             em("constexpr int F2_CAP = 256;")
@@ -747,6 +835,13 @@ class TPGenerator:
                 self._emit_fwd2_group(em, gid, ps)
         for gid, ps in enumerate(self.bwd_groups):
             self._emit_bwd_group(em, gid, ps)
+        self.use_ring_bwd = bool(self.opts.bwd_ring and sig.weight_numel % 4 == 0 and len(self.bwd_groups) >= 2)
+        if self.use_ring_bwd:
+            em(f"constexpr int B2_STAGES = {self.opts.ring_stages};")
+            em("constexpr int B2_CAP = 256;")
+            em("__device__ __forceinline__ void cta_sync_b() { asm volatile(\"bar.sync 1, %0;\" ::\"n\"(32 * NGB) : \"memory\"); }")
+            for gid, ps in enumerate(self.bwd_groups):
+                self._emit_bwd2_group(em, gid, ps)
         mbf = f", {self.opts.min_blocks_fwd}" if self.opts.min_blocks_fwd else ""
         mbb = f", {self.opts.min_blocks_bwd}" if self.opts.min_blocks_bwd else ""
         # unwritten output chunks (irreps_out entries no instruction writes) must be zero-filled
@@ -845,6 +940,41 @@ class TPGenerator:
         em("default: break;")
         em.end()
         em.end()
+        if self.use_ring_bwd:
+            minb2 = max(1, min(16, 384 // (32 * len(self.bwd_groups))))
+            em.block(
+                f"template <bool WANT_GX> __global__ void __launch_bounds__(32 * NGB, {minb2}) tp_bwd2_kernel("
+                "const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w, "
+                "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
+                "const int64_t* __restrict__ src, const float* __restrict__ gout, int64_t N, "
+                "float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gw)"
+            )
+            em("extern __shared__ __align__(16) uint8_t b2_smem[];")
+            em("constexpr int LPE = VT<float>::LPE, CPT = VT<float>::CPT, EPW = VT<float>::EPW;")
+            em(f"constexpr size_t RING_FLOATS = (size_t)B2_STAGES * EPW * {sig.weight_numel};")
+            em("float* ring = reinterpret_cast<float*>(b2_smem);")
+            em("uint64_t* full = reinterpret_cast<uint64_t*>(b2_smem + RING_FLOATS * sizeof(float));")
+            em("uint64_t* empty = full + B2_STAGES;")
+            em("int64_t* eids = reinterpret_cast<int64_t*>(empty + B2_STAGES);")
+            em("int64_t* srcs = eids + B2_CAP;")
+            em("const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
+            em("const int64_t n = blockIdx.x;")
+            em("const int cb = blockIdx.y;")
+            em("const int sub = lane / LPE, cl = lane % LPE;")
+            em("const int ch0 = (cb * LPE + cl) * CPT;")
+            em("const int64_t beg = row_ptr[n], end = row_ptr[n + 1];")
+            em.block("if (threadIdx.x == 0)")
+            em("for (int s_ = 0; s_ < B2_STAGES; ++s_) { mbar_init(&full[s_], 1); mbar_init(&empty[s_], NGB); }")
+            em("fence_barrier_init();")
+            em.end()
+            em("__syncthreads();")
+            em.block("switch (warp)")
+            for gid in range(len(self.bwd_groups)):
+                em(f"case {gid}: bwd2_g{gid}<WANT_GX>(x, y, w, perm, src, gout, n, beg, end, ch0, sub, cl, warp, lane, "
+                   "ring, full, empty, eids, srcs, gx, gy, gw); break;")
+            em("default: break;")
+            em.end()
+            em.end()
         em("}  // namespace")
         em()
         # C entry points
@@ -889,6 +1019,24 @@ class TPGenerator:
         em("(void)E;")
         em("if (N <= 0) return 0;")
         em("dim3 block(32 * NWARP);")
+        if self.use_ring_bwd:
+            lpe_f2, epw_f2, cb_f2 = self.geometry(2)
+            smemb = self.opts.ring_stages * epw_f2 * sig.weight_numel * 4 + 2 * self.opts.ring_stages * 8 + 256 * 16
+            em.block("if (dtype == 0)")
+            em(f"constexpr int B2_SMEM = {smemb};")
+            em("static bool attr_set = false;")
+            em.block("if (!attr_set)")
+            em("cudaFuncSetAttribute(tp_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);")
+            em("cudaFuncSetAttribute(tp_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);")
+            em("attr_set = true;")
+            em.end()
+            em("dim3 grid2((unsigned)N, VT<float>::CB), block2(32 * NGB);")
+            a2 = ("(const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, (const float*)gout, N, "
+                  "(float*)gx, (float*)gy, (float*)gw")
+            em(f"if (gx) tp_bwd2_kernel<true><<<grid2, block2, B2_SMEM, st>>>({a2});")
+            em(f"else tp_bwd2_kernel<false><<<grid2, block2, B2_SMEM, st>>>({a2});")
+            em("return (int)cudaGetLastError();")
+            em.end()
         for dt, name in ((0, "float"), (1, "double")):
             em.block(f"if (dtype == {dt})")
             em(f"dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGB * VT<{name}>::CB);")

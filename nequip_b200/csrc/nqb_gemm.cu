@@ -44,7 +44,7 @@ struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
   int64_t a_off, c_off, b_off, rs_off;  // element offsets from the base pointers; rs_off = ROW of the
                                         // [R, rs_ld] row-scale matrix (< 0: no row scale)
   int64_t lda, ldc, K, N;
-  int64_t kchunks, ntiles, tile0, flags;  // flags bit0: accumulate into C
+  int64_t kchunks, ntiles, tile0, flags;  // flags: see the epilogue
 };
 
 struct Smem {
@@ -192,7 +192,10 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
       const int ncols = min(TN, N - w.nt * TN);
       const int64_t ldc = d->ldc;
       float* C = c_base + d->c_off + (int64_t)w.nt * TN;
-      const bool accumulate = (d->flags & 1) != 0;
+      // flags: bit0 read-modify-write accumulate (single writer per element within the launch),
+      //        bit1 rows whose row scale is zero are not touched (disjoint row-masked writers),
+      //        bit2 accumulate with red.global.add (several problems of this launch add into the same C)
+      const bool accumulate = (d->flags & 1) != 0, skipz = (d->flags & 2) != 0, atomic = (d->flags & 4) != 0;
       float rs = 1.0f;
       if (d->rs_off >= 0) {
         const int64_t m = w.m0 + row;
@@ -213,14 +216,20 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
             const int rr = p * 4 + (lane >> 3), u = lane & 7;
             const int64_t m = w.m0 + ew * 32 + rr;
             const int col = cb * 32 + u * 4;
-            if (m < M && col < ncols) {
+            const float rsr = __shfl_sync(0xffffffffu, rs, rr);
+            if (m < M && col < ncols && !(skipz && rsr == 0.f)) {
               float4 val = st[rr * 8 + (u ^ (rr & 7))];
               float4* dst = reinterpret_cast<float4*>(C + m * ldc + col);
-              if (accumulate) {
-                const float4 old = *dst;
-                val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+              if (atomic) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y), "f"(val.z),
+                             "f"(val.w) : "memory");
+              } else {
+                if (accumulate) {
+                  const float4 old = *dst;
+                  val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                }
+                *dst = val;
               }
-              *dst = val;
             }
           }
           __syncwarp();

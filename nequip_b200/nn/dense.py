@@ -62,7 +62,10 @@ class IrrepsLinearGemm:
         self.d_in, self.d_out = fin.dim, fout.dim
         fwd: List[ops.GemmProblem] = []
         bwd: List[ops.GemmProblem] = []
-        out_written, in_written = set(), set()
+        # problems of one launch run concurrently: a target written by more than one problem is
+        # zero-initialised and every writer adds with red.global.add; single writers store plainly
+        n_out = {o: sum(1 for (_, o2, _, _) in lin.instr if o2 == o) for o in range(len(fout))}
+        n_in = {i: sum(1 for (i2, _, _, _) in lin.instr if i2 == i) for i in range(len(fin))}
         for (i, o, off, pw) in lin.instr:
             mi, ir = fin[i]
             mo = fout[o][0]
@@ -70,13 +73,11 @@ class IrrepsLinearGemm:
             for c in range(ir.dim):
                 a_off, c_off = in_off[i] + c * mi, out_off[o] + c * mo
                 fwd.append(ops.GemmProblem(a_off, self.d_in, c_off, self.d_out, W, scale=pw * extra_scale,
-                                           accumulate=(o, c) in out_written))
-                out_written.add((o, c))
+                                           atomic=n_out[o] > 1))
                 bwd.append(ops.GemmProblem(c_off, self.d_out, a_off, self.d_in, W, scale=pw * extra_scale, transposed=True,
-                                           accumulate=(i, c) in in_written))
-                in_written.add((i, c))
-        self.zero_out = any((o, c) not in out_written for o, (mo, ir) in enumerate(fout) for c in range(ir.dim))
-        self.zero_in = any((i, c) not in in_written for i, (mi, ir) in enumerate(fin) for c in range(ir.dim))
+                                           atomic=n_in[i] > 1))
+        self.zero_out = any(n != 1 for n in n_out.values())
+        self.zero_in = any(n != 1 for n in n_in.values())
         self.fwd = ops.GroupedGemm(fwd, device)
         self.bwd = ops.GroupedGemm(bwd, device)
 
@@ -101,7 +102,6 @@ class SelfConnectionGemm:
         self.T = type_table.shape[0]
         fwd: List[ops.GemmProblem] = []
         bwd: List[ops.GemmProblem] = []
-        in_written = set()
         tt = type_table.detach()
         for (i, o, off, pw) in sc.instr:
             mi, ir = fin[i]
@@ -112,12 +112,17 @@ class SelfConnectionGemm:
                 for c in range(ir.dim):
                     a_off, c_off = in_off[i] + c * mi, out_off[o] + c * mo
                     # row scale = row t of one-hot^T [T, M]
+                    # forward: each atom row belongs to exactly one type -> the T problems of one (pair,
+                    # component) write disjoint rows; read-modify-write onto linear_2's output is race free
+                    # as long as only ONE in-chunk feeds an out chunk, otherwise add atomically
+                    multi_o = sum(1 for (_, o2, _, _) in sc.instr if o2 == o) > 1
                     fwd.append(ops.GemmProblem(a_off, self.d_in, c_off, self.d_out, weff[t].contiguous(), scale=pw,
-                                               accumulate=True, rs_off=t))
+                                               accumulate=not multi_o, atomic=multi_o, rs_off=t, skip_zero_rows=True))
+                    multi_i = sum(1 for (i2, _, _, _) in sc.instr if i2 == i) > 1
                     bwd.append(ops.GemmProblem(c_off, self.d_out, a_off, self.d_in, weff[t].contiguous(), scale=pw,
-                                               transposed=True, accumulate=(i, c) in in_written, rs_off=t))
-                    in_written.add((i, c))
-        self.zero_in = any((i, c) not in in_written for i, (mi, ir) in enumerate(fin) for c in range(ir.dim))
+                                               transposed=True, accumulate=not multi_i, atomic=multi_i, rs_off=t,
+                                               skip_zero_rows=True))
+        self.zero_in = True  # backward accumulates (row-masked) into a zero-initialised gradient
         self.fwd = ops.GroupedGemm(fwd, device)
         self.bwd = ops.GroupedGemm(bwd, device)
 

@@ -403,8 +403,10 @@ class GemmProblem:
     B: torch.Tensor  # [K, N] (or [N, K] when transposed=True), float32
     scale: float = 1.0
     transposed: bool = False
-    accumulate: bool = False
+    accumulate: bool = False  # C += ... (read-modify-write; at most ONE problem of the launch may touch an element)
     rs_off: int = -1  # row of the [R, M] row-scale matrix, -1 = none
+    skip_zero_rows: bool = False  # rows with row scale 0 are left untouched (disjoint row-masked writers)
+    atomic: bool = False  # C += ... with red.global.add (several problems of one launch add into the same C)
 
 
 class GroupedGemm:
@@ -429,7 +431,7 @@ class GroupedGemm:
                                            _stream()), "nqb_gemm_prepare")
             kchunks, ntiles = (K + 31) // 32, (N + 127) // 128
             rows.append([p.a_off, p.c_off, b_off, p.rs_off, p.lda, p.ldc, K, N, kchunks, ntiles, tile0,
-                         1 if p.accumulate else 0])
+                         (1 if p.accumulate else 0) | (2 if p.skip_zero_rows else 0) | (4 if p.atomic else 0)])
             blobs.append(prep)
             b_off += nfl
             tile0 += ntiles

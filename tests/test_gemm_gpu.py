@@ -41,12 +41,14 @@ def test_grouped_strided_with_rowscale():
     X = torch.randn(M, D_in, generator=g)
     W0, W1 = torch.randn(64, 128, generator=g), torch.randn(32, 16, generator=g)
     mask = (torch.rand(2, M, generator=g) > 0.5).float()
-    probs = [ops.GemmProblem(0, D_in, 0, D_out, W0)]
+    # problems of one launch run concurrently: the two writers of columns [0,128) both add atomically
+    # onto a zero-initialised target; the three 16-column targets have a single plain writer each
+    probs = [ops.GemmProblem(0, D_in, 0, D_out, W0, atomic=True)]
     for i in range(3):
         probs.append(ops.GemmProblem(64 + 32 * i, D_in, 128 + 16 * i, D_out, W1, scale=0.5))
-    probs.append(ops.GemmProblem(0, D_in, 0, D_out, W0, accumulate=True, rs_off=1))  # masked by mask[1]
+    probs.append(ops.GemmProblem(0, D_in, 0, D_out, W0, atomic=True, rs_off=1, skip_zero_rows=True))  # masked by mask[1]
     gg = ops.GroupedGemm(probs, "cuda")
-    out = torch.empty(M, D_out, device="cuda")
+    out = torch.zeros(M, D_out, device="cuda")
     gg.run(X.cuda(), out, M, rowscale=mask.cuda().contiguous())
     Xd = X.double()
     ref = torch.empty(M, D_out, dtype=torch.float64)
@@ -55,3 +57,21 @@ def test_grouped_strided_with_rowscale():
         ref[:, 128 + 16 * i: 144 + 16 * i] = 0.5 * (Xd[:, 64 + 32 * i: 96 + 32 * i] @ W1.double())
     err = (out.cpu().double() - ref).abs().max().item()
     assert err <= 2e-6 * ref.abs().max().item(), err
+
+
+@pytest.mark.timeout(180)
+def test_row_masked_disjoint_writers_accumulate_onto_base():
+    """The self-connection pattern: T row-masked problems (one-hot rows) accumulate onto an existing tensor."""
+    g = torch.Generator().manual_seed(6)
+    M, K, N, T = 1001, 64, 64, 3
+    X = torch.randn(M, K, generator=g)
+    Ws = [torch.randn(K, N, generator=g) for _ in range(T)]
+    types = torch.randint(0, T, (M,), generator=g)
+    onehot_t = torch.nn.functional.one_hot(types, T).float().t().contiguous()
+    base = torch.randn(M, N, generator=g)
+    probs = [ops.GemmProblem(0, K, 0, N, Ws[t], accumulate=True, rs_off=t, skip_zero_rows=True) for t in range(T)]
+    gg = ops.GroupedGemm(probs, "cuda")
+    out = base.clone().cuda()
+    gg.run(X.cuda(), out, M, rowscale=onehot_t.cuda())
+    ref = base.double() + torch.stack([X[m].double() @ Ws[int(types[m])].double() for m in range(M)])
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
