@@ -1,0 +1,74 @@
+// Microbenchmark: cycles per tcgen05.mma (SS operands, SWIZZLE_NONE K-major canonical layout) for
+// kind::tf32 (K=8) and kind::f16/bf16 (K=16), M=128, several N; one CTA per SM, one issuing thread.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../nequip_b200/csrc/nqb_tc.cuh"
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// MODE 0: tf32, 1: bf16.  lbo/sbo: descriptor strides in bytes.  spread: operand address varies per MMA.
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) k(long long* out, int nmma, int N, uint32_t lbo, uint32_t sbo, int spread) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tbase;
+  for (int i = threadIdx.x; i < 128 * 1024 / 4; i += blockDim.x) ((float*)sm)[i] = 0.f;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(&tbase, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (MODE == 0) ? make_idesc(128, N) : idesc_bf16(128, N);
+    const uint32_t a0 = smem_u32(sm), b0 = smem_u32(sm + 64 * 1024);
+    const long long t0 = clock64();
+    for (int i = 0; i < nmma; ++i) {
+      const uint32_t off = spread ? (uint32_t)((i & 3) * 256) : 0u;
+      const uint64_t da = make_desc(a0 + off, lbo, sbo), db = make_desc(b0 + off, lbo, sbo);
+      const uint32_t d = tbase + (uint32_t)((i & 1) * 256);
+      if (MODE == 0) umma_tf32(d, da, db, idesc, i > 1);
+      else umma_bf16(d, da, db, idesc, i > 1);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tbase, 512);
+}
+
+template <int MODE> void run(const char* name, int N, uint32_t lbo, uint32_t sbo, int spread, long long* d_out, int nsm) {
+  const int nmma = 2048;
+  cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  k<MODE><<<nsm, 128, 160 * 1024>>>(d_out, nmma, N, lbo, sbo, spread);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: ERROR %s\n", name, cudaGetErrorString(e)); return; }
+  long long h[256];
+  cudaMemcpy(h, d_out, nsm * sizeof(long long), cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < nsm; ++i) avg += (double)h[i]; avg /= nsm;
+  const int K = MODE == 0 ? 8 : 16;
+  printf("%-44s N=%3d  %7.1f cycles/MMA   %8.1f flop/clk/SM\n", name, N, avg / nmma, 2.0 * 128 * N * K * nmma / avg);
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  int nsm = p.multiProcessorCount;
+  long long* d_out; cudaMalloc(&d_out, 256 * sizeof(long long));
+  printf("%s, %d SMs (all SMs issue concurrently)\n", p.name, nsm);
+  for (int N : {32, 64, 128, 256}) run<0>("tf32 SS no-swizzle LBO=128 SBO=1024 (chunk K=32)", N, 128, 1024, 1, d_out, nsm);
+  for (int N : {32, 128}) run<0>("tf32 SS no-swizzle LBO=128 SBO=4096 (K=128)", N, 128, 4096, 1, d_out, nsm);
+  for (int N : {128}) run<0>("tf32 SS no-swizzle same operands", N, 128, 1024, 0, d_out, nsm);
+  for (int N : {32, 64, 128, 256}) run<1>("bf16 SS no-swizzle LBO=128 SBO=1024", N, 128, 1024, 1, d_out, nsm);
+  run<0>("tf32 on ONE SM only", 128, 128, 1024, 1, d_out, 1);
+  return 0;
+}

@@ -14,11 +14,11 @@ from nequip_b200.codegen import GenOptions  # noqa: E402
 from nequip_b200.known_signatures import nequip_layer_signatures  # noqa: E402
 
 VARIANTS = {
-    "irmul_ring6": GenOptions(layout="ir_mul"),
-    "irmul_noring": GenOptions(layout="ir_mul", fwd_ring=False),
-    "irmul_ring4": GenOptions(layout="ir_mul", ring_stages=4),
-    "irmul_ring8": GenOptions(layout="ir_mul", ring_stages=8),
-    "mulir_ring6": GenOptions(layout="mul_ir"),
+    "irmul": GenOptions(layout="ir_mul"),
+    "irmul_nobwdring": GenOptions(layout="ir_mul", bwd_ring=False),
+    "irmul_b16": GenOptions(layout="ir_mul", acc_cap_bwd=16),
+    "irmul_b32": GenOptions(layout="ir_mul", acc_cap_bwd=32),
+    "irmul_st6": GenOptions(layout="ir_mul", ring_stages=6),
 }
 _OLD = {
     "nopf": GenOptions(prefetch=False, idx_ahead=False),
