@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 12
+CODEGEN_VERSION = 13
 
 
 # ---------------------------------------------------------------------------
@@ -165,7 +165,7 @@ class TPSignature:
 class GenOptions:
     nwarp: int = 4  # warps (= destination nodes) per CTA
     acc_cap: int = 32  # max output components per channel held by one warp (forward)
-    acc_cap_bwd: int = 24
+    acc_cap_bwd: int = 32
     prefetch: bool = True  # software-pipelined edge loop (loads of edge i+1 in flight during compute of i)
     idx_ahead: bool = True  # edge/source indices fetched two iterations ahead (breaks the dependent-load chain)
     min_blocks_fwd: int = 4  # __launch_bounds__ minBlocksPerSM (0 = unset); occupancy beats everything else here

@@ -36,7 +36,8 @@ namespace {
 constexpr int TM = 128;          // rows per tile
 constexpr int TN = 128;          // max columns per tile
 constexpr int KC = 32;           // K chunk
-constexpr int STAGES = 3;
+constexpr int ASTAGES = 2;       // A ring (the producers hold one more chunk in registers)
+constexpr int BSLOTS = 4;        // B slots: a ring when K > 128, resident per N-tile when K <= 128
 constexpr int SEG_CHUNKS = 10;   // chunks per accumulation segment (40 accumulate steps on the hi*hi accumulator)
 constexpr int BLOCK_FLOATS = 2 * TN * KC;  // one prepared weight block: [hi | lo] x [128 x 32]
 
@@ -48,10 +49,11 @@ struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
 };
 
 struct Smem {
-  float a[STAGES][2 * TM * KC];  // 3 x 32 KB
-  float b[STAGES][BLOCK_FLOATS];  // 3 x 32 KB
-  float stage[4][32 * 32];       // epilogue staging, one 32x32 tile per warp (swizzled)
-  uint64_t a_full[STAGES], b_full[STAGES], empty[STAGES];
+  float a[ASTAGES][2 * TM * KC];   // 2 x 32 KB
+  float b[BSLOTS][BLOCK_FLOATS];   // 4 x 32 KB
+  float stage[4][32 * 32];         // epilogue staging, one 32x32 tile per warp (swizzled)
+  uint64_t a_full[ASTAGES], a_empty[ASTAGES];
+  uint64_t b_full[BSLOTS], b_empty[BSLOTS];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
@@ -62,22 +64,40 @@ __device__ __forceinline__ const GemmDesc* find_desc(const GemmDesc* d, int nd, 
   return d + i;
 }
 
-struct WorkItem {  // decoded (M-tile, N-tile) work item
-  const GemmDesc* d;
-  int64_t m0;
-  int nt, kchunks, K;
+// Work schedule (identical in every role).  T = N-tiles over all problems, G = CTAs.
+//   T <= G: CTA b owns ONE N-tile q = b % T and the M-tiles r, r+R, r+2R, ... (r = b / T, R = G / T):
+//           the T CTAs that share r sweep the same M-tiles in lockstep (A tiles are shared in L2)
+//           and the weight tile of a K <= 128 problem stays resident in shared memory;
+//   T >  G: CTA b owns N-tiles b, b+G, ... and sweeps all M-tiles for each.
+struct Sched {
+  int q, q_step, nq_total;
+  int64_t m_start, m_step;
+  __device__ Sched(int b, int G, int T) {
+    if (T <= G) {
+      const int R = G / T;
+      q = (b < T * R) ? (b % T) : T;  // T = no work
+      q_step = T;
+      m_start = b / T;
+      m_step = R;
+    } else {
+      q = b; q_step = G; m_start = 0; m_step = 1;
+    }
+    nq_total = T;
+  }
 };
 
-__device__ __forceinline__ bool decode_work(int64_t wi, int64_t nwork, const GemmDesc* descs, int ndesc, int ntiles_total,
-                                            WorkItem& w) {
-  if (wi >= nwork) return false;
-  const int q = (int)(wi % ntiles_total);
+struct WorkQ {  // one N-tile of one problem
+  const GemmDesc* d;
+  int nt, kchunks, K, ncols;
+  bool resident;
+};
+__device__ __forceinline__ void decode_q(const GemmDesc* descs, int ndesc, int q, WorkQ& w) {
   w.d = find_desc(descs, ndesc, q);
   w.nt = q - (int)w.d->tile0;
-  w.m0 = (wi / ntiles_total) * TM;
   w.kchunks = (int)w.d->kchunks;
   w.K = (int)w.d->K;
-  return true;
+  w.ncols = min(TN, (int)w.d->N - w.nt * TN);
+  w.resident = w.kchunks <= BSLOTS;
 }
 
 __global__ void __launch_bounds__(320, 1)
@@ -88,10 +108,10 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t mtiles = (M + TM - 1) / TM;
-  const int64_t nwork = mtiles * ntiles_total;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&S.a_full[s], 128); mbar_init(&S.b_full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < ASTAGES; ++s) { mbar_init(&S.a_full[s], 128); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < BSLOTS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 128); }
     fence_barrier_init();
   }
@@ -100,66 +120,62 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
+  const Sched sch(blockIdx.x, gridDim.x, ntiles_total);
 
   if (warp < 4) {
     // =========================== A producer: global -> registers (one chunk ahead) -> split -> smem ======
     const int r8 = lane & 7, kq = lane >> 3;
-    auto load_chunk = [&](const WorkItem& w, int c, float4* v) {
+    uint32_t it = 0;
+    float4 v[8], vn[8];
+    for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
+      WorkQ w;
+      decode_q(descs, ndesc, q, w);
       const float* A = a_base + w.d->a_off;
       const int64_t lda = w.d->lda;
+      auto load_chunk = [&](int64_t mt, int c, float4* dst) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int64_t m = w.m0 + warp * 32 + g * 8 + r8;
+        for (int g = 0; g < 4; ++g) {
+          const int64_t m = mt * TM + warp * 32 + g * 8 + r8;
 #pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          const int k = c * KC + (hp * 4 + kq) * 4;
-          v[g * 2 + hp] = (m < M && k < w.K) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + k))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int hp = 0; hp < 2; ++hp) {
+            const int k = c * KC + (hp * 4 + kq) * 4;
+            dst[g * 2 + hp] = (m < M && k < w.K) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + k))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-      }
-    };
-    WorkItem cur, nxt;
-    int64_t wi = blockIdx.x;
-    bool have = decode_work(wi, nwork, descs, ndesc, ntiles_total, cur);
-    int c = 0;
-    float4 v[8], vn[8];
-    if (have) load_chunk(cur, 0, v);
-    uint32_t it = 0;
-    while (have) {
-      // coordinates of the following chunk (possibly the first chunk of the next work item)
-      bool have_n = true;
-      int cn = c + 1;
-      int64_t win = wi;
-      nxt = cur;
-      if (cn == cur.kchunks) {
-        cn = 0;
-        win = wi + gridDim.x;
-        have_n = decode_work(win, nwork, descs, ndesc, ntiles_total, nxt);
-      }
-      if (have_n) load_chunk(nxt, cn, vn);
-      const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-      if (it >= STAGES) mbar_wait(&S.empty[s], ph ^ 1);
-      float* ahi = S.a[s];
-      float* alo = S.a[s] + TM * KC;
+      };
+      int64_t mt = sch.m_start;
+      int c = 0;
+      if (mt < mtiles) load_chunk(mt, 0, v);
+      while (mt < mtiles) {
+        int cn = c + 1;
+        int64_t mtn = mt;
+        if (cn == w.kchunks) { cn = 0; mtn = mt + sch.m_step; }
+        if (mtn < mtiles) load_chunk(mtn, cn, vn);
+        const uint32_t s = it % ASTAGES, ph = (it / ASTAGES) & 1;
+        if (it >= ASTAGES) mbar_wait(&S.a_empty[s], ph ^ 1);
+        float* ahi = S.a[s];
+        float* alo = S.a[s] + TM * KC;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 4; ++g) {
 #pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          const int r = warp * 32 + g * 8 + r8, kg = hp * 4 + kq;
-          const float4 a = v[g * 2 + hp];
-          const float4 hi = make_float4(tf32_rn(a.x), tf32_rn(a.y), tf32_rn(a.z), tf32_rn(a.w));
-          const float4 lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
-          const int off = (r >> 3) * (KC / 4 * 32) + kg * 32 + (r & 7) * 4;
-          *reinterpret_cast<float4*>(ahi + off) = hi;
-          *reinterpret_cast<float4*>(alo + off) = lo;
+          for (int hp = 0; hp < 2; ++hp) {
+            const int r = warp * 32 + g * 8 + r8, kg = hp * 4 + kq;
+            const float4 a = v[g * 2 + hp];
+            const float4 hi = make_float4(tf32_rn(a.x), tf32_rn(a.y), tf32_rn(a.z), tf32_rn(a.w));
+            const float4 lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
+            const int off = (r >> 3) * (KC / 4 * 32) + kg * 32 + (r & 7) * 4;
+            *reinterpret_cast<float4*>(ahi + off) = hi;
+            *reinterpret_cast<float4*>(alo + off) = lo;
+          }
         }
-      }
-      fence_proxy_async();
-      mbar_arrive(&S.a_full[s]);
-      ++it;
+        fence_proxy_async();
+        mbar_arrive(&S.a_full[s]);
+        ++it;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = vn[q];
-      cur = nxt; c = cn; wi = win; have = have_n;
+        for (int j = 0; j < 8; ++j) v[j] = vn[j];
+        c = cn; mt = mtn;
+      }
     }
   } else if (warp < 8) {
     // =========================== epilogue: TMEM segments -> registers -> C ============================
@@ -167,91 +183,102 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
     const int row = ew * 32 + lane;    // accumulator row owned by this thread
     uint32_t gseg = 0;
     float acc[TN];
-    WorkItem w;
-    for (int64_t wi = blockIdx.x; decode_work(wi, nwork, descs, ndesc, ntiles_total, w); wi += gridDim.x) {
-      const int nseg = (w.kchunks + SEG_CHUNKS - 1) / SEG_CHUNKS;
-#pragma unroll
-      for (int j = 0; j < TN; ++j) acc[j] = 0.f;
-      for (int sidx = 0; sidx < nseg; ++sidx, ++gseg) {
-        const uint32_t buf = gseg & 1;
-        mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int cb = 0; cb < TN / 16; ++cb) {
-          float hh[16], xx[16];
-          tmem_ld16(tmem + ((uint32_t)(ew * 32) << 16) + buf * 256 + cb * 16, hh);
-          tmem_ld16(tmem + ((uint32_t)(ew * 32) << 16) + buf * 256 + 128 + cb * 16, xx);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += hh[j] + xx[j];
-        }
-        tc_fence_before();
-        mbar_arrive(&S.acc_empty[buf]);
-      }
+    for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
+      WorkQ w;
+      decode_q(descs, ndesc, q, w);
       const GemmDesc* d = w.d;
-      const int N = (int)d->N;
-      const int ncols = min(TN, N - w.nt * TN);
+      const int nseg = (w.kchunks + SEG_CHUNKS - 1) / SEG_CHUNKS;
+      const int ncols = w.ncols;
       const int64_t ldc = d->ldc;
       float* C = c_base + d->c_off + (int64_t)w.nt * TN;
       // flags: bit0 read-modify-write accumulate (single writer per element within the launch),
       //        bit1 rows whose row scale is zero are not touched (disjoint row-masked writers),
       //        bit2 accumulate with red.global.add (several problems of this launch add into the same C)
       const bool accumulate = (d->flags & 1) != 0, skipz = (d->flags & 2) != 0, atomic = (d->flags & 4) != 0;
-      float rs = 1.0f;
-      if (d->rs_off >= 0) {
-        const int64_t m = w.m0 + row;
-        rs = (m < M) ? __ldg(rs_base + d->rs_off * rs_ld + m) : 0.f;
-      }
-      float4* st = reinterpret_cast<float4*>(S.stage[ew]);
+      for (int64_t mt = sch.m_start; mt < mtiles; mt += sch.m_step) {
+        const int64_t m0 = mt * TM;
 #pragma unroll
-      for (int cb = 0; cb < TN / 32; ++cb) {
-        if (cb * 32 < ncols) {
-          const int rl = lane;
+        for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+        for (int sidx = 0; sidx < nseg; ++sidx, ++gseg) {
+          const uint32_t buf = gseg & 1;
+          mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1);
+          tc_fence_after();
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            st[rl * 8 + (u ^ (rl & 7))] = make_float4(acc[cb * 32 + 4 * u] * rs, acc[cb * 32 + 4 * u + 1] * rs,
-                                                      acc[cb * 32 + 4 * u + 2] * rs, acc[cb * 32 + 4 * u + 3] * rs);
-          __syncwarp();
+          for (int cb = 0; cb < TN / 16; ++cb) {
+            float hh[16], xx[16];
+            tmem_ld16(tmem + ((uint32_t)(ew * 32) << 16) + buf * 256 + cb * 16, hh);
+            tmem_ld16(tmem + ((uint32_t)(ew * 32) << 16) + buf * 256 + 128 + cb * 16, xx);
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            const int rr = p * 4 + (lane >> 3), u = lane & 7;
-            const int64_t m = w.m0 + ew * 32 + rr;
-            const int col = cb * 32 + u * 4;
-            const float rsr = __shfl_sync(0xffffffffu, rs, rr);
-            if (m < M && col < ncols && !(skipz && rsr == 0.f)) {
-              float4 val = st[rr * 8 + (u ^ (rr & 7))];
-              float4* dst = reinterpret_cast<float4*>(C + m * ldc + col);
-              if (atomic) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y), "f"(val.z),
-                             "f"(val.w) : "memory");
-              } else {
-                if (accumulate) {
-                  const float4 old = *dst;
-                  val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+            for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += hh[j] + xx[j];
+          }
+          tc_fence_before();
+          mbar_arrive(&S.acc_empty[buf]);
+        }
+        float rs = 1.0f;
+        if (d->rs_off >= 0) {
+          const int64_t m = m0 + row;
+          rs = (m < M) ? __ldg(rs_base + d->rs_off * rs_ld + m) : 0.f;
+        }
+        float4* st = reinterpret_cast<float4*>(S.stage[ew]);
+#pragma unroll
+        for (int cb = 0; cb < TN / 32; ++cb) {
+          if (cb * 32 < ncols) {
+            const int rl = lane;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              st[rl * 8 + (u ^ (rl & 7))] = make_float4(acc[cb * 32 + 4 * u] * rs, acc[cb * 32 + 4 * u + 1] * rs,
+                                                        acc[cb * 32 + 4 * u + 2] * rs, acc[cb * 32 + 4 * u + 3] * rs);
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const int rr = p * 4 + (lane >> 3), u = lane & 7;
+              const int64_t m = m0 + ew * 32 + rr;
+              const int col = cb * 32 + u * 4;
+              const float rsr = __shfl_sync(0xffffffffu, rs, rr);
+              if (m < M && col < ncols && !(skipz && rsr == 0.f)) {
+                float4 val = st[rr * 8 + (u ^ (rr & 7))];
+                float4* dst = reinterpret_cast<float4*>(C + m * ldc + col);
+                if (atomic) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
+                               "f"(val.z), "f"(val.w) : "memory");
+                } else {
+                  if (accumulate) {
+                    const float4 old = *dst;
+                    val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                  }
+                  *dst = val;
                 }
-                *dst = val;
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
   } else if (warp == 8) {
     // =========================== weight-chunk loader ===================================================
     if (lane == 0) {
-      uint32_t it = 0;
-      WorkItem w;
-      for (int64_t wi = blockIdx.x; decode_work(wi, nwork, descs, ndesc, ntiles_total, w); wi += gridDim.x) {
-        const int ncols = min(TN, (int)w.d->N - w.nt * TN);
-        const int nrows = (ncols + 15) & ~15;  // MMA N (multiple of 16); prepared blocks are zero padded
+      uint32_t bcount[BSLOTS] = {0, 0, 0, 0};  // loads issued per slot
+      uint32_t bit = 0;                         // ring position (streaming mode)
+      auto load_slot = [&](int slot, const float* src, uint32_t bytes) {
+        if (bcount[slot] > 0) mbar_wait(&S.b_empty[slot], (bcount[slot] - 1) & 1);
+        mbar_expect_tx(&S.b_full[slot], 2 * bytes);
+        bulk_g2s(S.b[slot], src, bytes, &S.b_full[slot]);
+        bulk_g2s(S.b[slot] + TN * KC, src + TN * KC, bytes, &S.b_full[slot]);
+        ++bcount[slot];
+      };
+      for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
+        WorkQ w;
+        decode_q(descs, ndesc, q, w);
+        const int nrows = (w.ncols + 15) & ~15;  // MMA N (multiple of 16); prepared blocks are zero padded
         const uint32_t bytes = (uint32_t)nrows * KC * sizeof(float);
         const float* B = b_base + w.d->b_off + (int64_t)w.nt * w.kchunks * BLOCK_FLOATS;
-        for (int c = 0; c < w.kchunks; ++c, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-          if (it >= STAGES) mbar_wait(&S.empty[s], ph ^ 1);
-          mbar_expect_tx(&S.b_full[s], 2 * bytes);
-          bulk_g2s(S.b[s], B + (int64_t)c * BLOCK_FLOATS, bytes, &S.b_full[s]);
-          bulk_g2s(S.b[s] + TN * KC, B + (int64_t)c * BLOCK_FLOATS + TN * KC, bytes, &S.b_full[s]);
+        if (sch.m_start >= mtiles) continue;
+        if (w.resident) {
+          for (int c = 0; c < w.kchunks; ++c) load_slot(c, B + (int64_t)c * BLOCK_FLOATS, bytes);
+        } else {
+          for (int64_t mt = sch.m_start; mt < mtiles; mt += sch.m_step)
+            for (int c = 0; c < w.kchunks; ++c, ++bit) load_slot(bit % BSLOTS, B + (int64_t)c * BLOCK_FLOATS, bytes);
         }
       }
     }
@@ -259,41 +286,59 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
     // =========================== MMA issuer ============================================================
     if (lane == 0) {
       constexpr uint32_t SBO = (KC / 4) * 128, LBO = 128;
-      uint32_t it = 0, gseg = 0;
-      WorkItem w;
-      for (int64_t wi = blockIdx.x; decode_work(wi, nwork, descs, ndesc, ntiles_total, w); wi += gridDim.x) {
-        const int ncols = min(TN, (int)w.d->N - w.nt * TN);
-        const int nmma = (ncols + 15) & ~15;
+      uint32_t it = 0, gseg = 0, bit = 0;
+      uint32_t bcount[BSLOTS] = {0, 0, 0, 0};  // loads consumed (waited for) per slot
+      for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
+        WorkQ w;
+        decode_q(descs, ndesc, q, w);
+        const int nmma = (w.ncols + 15) & ~15;
         const uint32_t idesc = make_idesc(TM, nmma);
-        for (int c0 = 0; c0 < w.kchunks; c0 += SEG_CHUNKS, ++gseg) {
-          const uint32_t buf = gseg & 1;
-          if (gseg >= 2) mbar_wait(&S.acc_empty[buf], ((gseg >> 1) - 1) & 1);
-          tc_fence_after();
-          const uint32_t d_hh = tmem + buf * 256, d_x = d_hh + 128;
-          uint32_t acc_hh = 0, acc_x = 0;
-          const int c1 = min(w.kchunks, c0 + SEG_CHUNKS);
-          for (int c = c0; c < c1; ++c, ++it) {
-            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-            mbar_wait(&S.a_full[s], ph);
-            mbar_wait(&S.b_full[s], ph);
+        bool first_mt = true;
+        for (int64_t mt = sch.m_start; mt < mtiles; mt += sch.m_step) {
+          for (int c0 = 0; c0 < w.kchunks; c0 += SEG_CHUNKS, ++gseg) {
+            const uint32_t buf = gseg & 1;
+            if (gseg >= 2) mbar_wait(&S.acc_empty[buf], ((gseg >> 1) - 1) & 1);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(S.a[s]), a_lo = a_hi + TM * KC * sizeof(float);
-            const uint32_t b_hi = smem_u32(S.b[s]), b_lo = b_hi + TN * KC * sizeof(float);
+            const uint32_t d_hh = tmem + buf * 256, d_x = d_hh + 128;
+            uint32_t acc_hh = 0, acc_x = 0;
+            const int c1 = min(w.kchunks, c0 + SEG_CHUNKS);
+            for (int c = c0; c < c1; ++c, ++it) {
+              const uint32_t s = it % ASTAGES, ph = (it / ASTAGES) & 1;
+              int slot;
+              if (w.resident) {
+                slot = c;
+                if (first_mt) { mbar_wait(&S.b_full[slot], bcount[slot] & 1); ++bcount[slot]; }
+              } else {
+                slot = bit % BSLOTS;
+                ++bit;
+                mbar_wait(&S.b_full[slot], bcount[slot] & 1);
+                ++bcount[slot];
+              }
+              mbar_wait(&S.a_full[s], ph);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(S.a[s]), a_lo = a_hi + TM * KC * sizeof(float);
+              const uint32_t b_hi = smem_u32(S.b[slot]), b_lo = b_hi + TN * KC * sizeof(float);
 #pragma unroll
-            for (int ks = 0; ks < KC / 8; ++ks) {
-              umma_tf32(d_hh, make_desc(a_hi + ks * 256, LBO, SBO), make_desc(b_hi + ks * 256, LBO, SBO), idesc, acc_hh);
-              acc_hh = 1;
-            }
+              for (int ks = 0; ks < KC / 8; ++ks) {
+                umma_tf32(d_hh, make_desc(a_hi + ks * 256, LBO, SBO), make_desc(b_hi + ks * 256, LBO, SBO), idesc, acc_hh);
+                acc_hh = 1;
+              }
 #pragma unroll
-            for (int ks = 0; ks < KC / 8; ++ks) {
-              umma_tf32(d_x, make_desc(a_lo + ks * 256, LBO, SBO), make_desc(b_hi + ks * 256, LBO, SBO), idesc, acc_x);
-              acc_x = 1;
-              umma_tf32(d_x, make_desc(a_hi + ks * 256, LBO, SBO), make_desc(b_lo + ks * 256, LBO, SBO), idesc, 1);
+              for (int ks = 0; ks < KC / 8; ++ks) {
+                umma_tf32(d_x, make_desc(a_lo + ks * 256, LBO, SBO), make_desc(b_hi + ks * 256, LBO, SBO), idesc, acc_x);
+                acc_x = 1;
+                umma_tf32(d_x, make_desc(a_hi + ks * 256, LBO, SBO), make_desc(b_lo + ks * 256, LBO, SBO), idesc, 1);
+              }
+              umma_commit(&S.a_empty[s]);
+              if (!w.resident) umma_commit(&S.b_empty[slot]);
             }
-            umma_commit(&S.empty[s]);
+            umma_commit(&S.acc_full[buf]);
           }
-          umma_commit(&S.acc_full[buf]);
+          first_mt = false;
         }
+        // resident weights: release the slots once every MMA of this N-tile has retired
+        if (w.resident && sch.m_start < mtiles)
+          for (int c = 0; c < w.kchunks; ++c) umma_commit(&S.b_empty[c]);
       }
     }
   }
