@@ -185,6 +185,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="li3po4_10k_l2_f64", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decomp", default="frames", choices=["frames", "halo"],
+                    help="N>1: 'frames' = one independent frame per GPU (the reference's DDP axis); 'halo' = ONE frame "
+                         "of N x atoms_per_gpu atoms, slab-partitioned, per-layer NCCL halo exchange + energy/force all-reduce")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one warm-up step, then ONE step between cudaProfilerStart/Stop (for ncu "
                          "--profile-from-start off); prints no bench line")
@@ -214,8 +217,36 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
 
-    # every rank owns its own frame (same size/density, different seed)
-    sysd, meta, mk = build_system(args.workload, seed=rank)
+    halo_mode = world > 1 and args.decomp == "halo"
+    if halo_mode:
+        # ONE frame of world x (22^3) atoms, elongated along x, slab decomposition (weak scaling)
+        from nequip_b200 import parallel as P
+
+        kind, ns, mk = WORKLOADS[args.workload]
+        pr = D.PRESETS[kind]
+        import numpy as np
+
+        a = (1.0 / pr["density"]) ** (1.0 / 3.0)
+        rng = np.random.default_rng(0)
+        gx, gy = np.arange(ns * world, dtype=np.float64), np.arange(ns, dtype=np.float64)
+        zz, yy, xx = np.meshgrid(gy, gy, gx, indexing="ij")
+        pos_np = (np.stack([xx.ravel(), yy.ravel(), zz.ravel()], 1) + 0.5 + rng.uniform(-0.22, 0.22, (xx.size, 3))) * a
+        cell_np = np.diag([ns * world * a, ns * a, ns * a])
+        ratios = np.asarray(pr["ratios"], dtype=np.float64)
+        types_np = np.random.default_rng(1).choice(len(ratios), size=pos_np.shape[0], p=ratios / ratios.sum())
+        ei_np, sh_np = D.neighbor_list(pos_np, cell_np, R_MAX)
+        full = {"pos": torch.from_numpy(pos_np), "cell": torch.from_numpy(cell_np),
+                "atom_types": torch.from_numpy(types_np.astype(np.int64)), "edge_index": torch.from_numpy(ei_np),
+                "edge_cell_shift": torch.from_numpy(sh_np)}
+        meta = dict(type_names=list(pr["type_names"]), avg_num_neighbors=float(ei_np.shape[1]) / pos_np.shape[0])
+        owner = P.slab_owner(full["pos"], world)
+        plan = P.make_plans(full["edge_index"], owner, world)[rank]
+        sysd = P.shard_data(full, plan)
+        n_total_atoms = pos_np.shape[0]
+        del full
+    else:
+        # every rank owns its own frame (same size/density, different seed)
+        sysd, meta, mk = build_system(args.workload, seed=rank)
     n_atoms, n_edges = sysd["pos"].shape[0], sysd["edge_index"].shape[1]
     model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
                               avg_num_neighbors=meta["avg_num_neighbors"], **mk).to(dev)
@@ -226,7 +257,13 @@ def main():
     resident = D.to_device(sysd, dev)
     e_buf = torch.zeros(1, dtype=torch.float64, device=dev)
 
+    if halo_mode:
+        halo = P.HaloExchange(plan, dev)
+
     def step_resident():
+        if halo_mode:
+            e, f = P.sharded_energy_forces(model, resident, plan, halo)
+            return {"total_energy": e, "forces": f}
         out = model(resident)
         if world > 1:
             e_buf.copy_(out["total_energy"].view(-1))
@@ -238,8 +275,12 @@ def main():
 
     def step_e2e():
         d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
-        out = model(d)
-        if world > 1:
+        if halo_mode:
+            e, f = P.sharded_energy_forces(model, d, plan, halo, reduce_forces=False)
+            out = {"total_energy": e, "forces": f}
+        else:
+            out = model(d)
+        if world > 1 and not halo_mode:
             e_buf.copy_(out["total_energy"].view(-1))
             dist.all_reduce(e_buf)
         f_host.copy_(out["forces"], non_blocking=True)
@@ -347,7 +388,7 @@ def main():
         cpu = cpu_baseline(args.workload)
 
     if rank == 0:
-        total_atoms = n_atoms * world
+        total_atoms = n_total_atoms if halo_mode else n_atoms * world
         line = {
             "metric": "atom-steps/sec (energy+forces)",
             "value": total_atoms / (ms_res * 1e-3),
@@ -364,7 +405,9 @@ def main():
             "config": {
                 "workload": args.workload,
                 "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges, "r_max": R_MAX, "parity": True, **mk,
-                "parallelism": f"dp{world} over frames (one {n_atoms}-atom frame per GPU)",
+                "parallelism": (f"halo{world}: one {total_atoms}-atom frame in {world} x-slabs, {plan.n_own} owned + "
+                                f"{plan.n_ghost} ghost atoms on rank 0, per-layer NCCL halo exchange" if halo_mode
+                                else f"dp{world} over frames (one {n_atoms}-atom frame per GPU)"),
                 "l2_policy": "inputs larger than L2 (edge weights of one layer: %.2f GB)" % (
                     n_edges * max(l.conv.tp_scatter.weight_numel for l in model.layers) * 4 / 1e9),
             },

@@ -136,6 +136,14 @@ int nqb_mlp_fwd(const float* emb, const float* W1s, const float* prep_fwd, int64
 int nqb_mlp_bwd(const float* emb, const float* W1s, const float* prep_bwd, const float* grad_w, int64_t E,
                 int num_bessel, int hidden, int W, float* grad_emb, nqb_stream_t st);
 
+/* First radial layer (K = 8, CUDA cores):  h[E,128] = silu(emb[E,8] @ W1s[8,128])  and
+ * grad_emb[E,8] = (grad_h * silu'(emb @ W1s)) @ W1s^T  (pre-activation recomputed, nothing saved).
+ * Together with nqb_gemm_grouped for the second layer this is ScalarMLPFunction (nequip/nn/mlp.py:80-195). */
+int nqb_mlp_hidden_fwd(const float* emb, const float* W1s, int64_t E, int num_bessel, int hidden, float* h,
+                       nqb_stream_t st);
+int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const float* grad_h, int64_t E, int num_bessel,
+                       int hidden, float* grad_emb, nqb_stream_t st);
+
 /* Grouped fp32-accurate GEMM on the tensor cores (tcgen05 kind::tf32, 3xTF32, segmented fp32
  * accumulation):  C_p[M, N_p] (+)= rowscale_p[m] * A_p[M, K_p] @ B_p[K_p, N_p]  for a list of problems
  * sharing M.  Replaces the dense algebra around the convolution: ScalarMLPFunction's torch.mm

@@ -15,7 +15,7 @@
 // step), so the two cross terms go to their own TMEM accumulator and long reductions are cut into
 // segments of SEG_CHUNKS*32 in K whose partial sums are added in registers (round-to-nearest).
 //
-// Roles per CTA (320 threads, persistent over (M-tile, N-tile) work items, N-tile fastest so that
+// Roles per CTA (384 threads = 3 warpgroups with setmaxnreg-rebalanced registers, persistent over (M-tile, N-tile) work items, N-tile fastest so that
 // the CTAs working on one A tile run together and share it in L2):
 //   warps 0-3  producers: stream the A chunk [128 x 32] through registers (coalesced 16-byte loads, one
 //              chunk ahead, across work-item boundaries), split hi/lo into the canonical K-major
@@ -100,7 +100,7 @@ __device__ __forceinline__ void decode_q(const GemmDesc* descs, int ndesc, int q
   w.resident = w.kchunks <= BSLOTS;
 }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const float* __restrict__ a_base,
          const float* __restrict__ b_base, float* __restrict__ c_base, const float* __restrict__ rs_base, int64_t rs_ld,
          int64_t M) {
@@ -122,7 +122,10 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   const uint32_t tmem = S.tmem_base;
   const Sched sch(blockIdx.x, gridDim.x, ntiles_total);
 
+  // register budget per warpgroup (launch: 65536 / 384 = 168 each): the epilogue keeps a 128-value row of
+  // partial sums in registers, the producers and the two single-lane roles need few
   if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     // =========================== A producer: global -> registers (one chunk ahead) -> split -> smem ======
     const int r8 = lane & 7, kq = lane >> 3;
     uint32_t it = 0;
@@ -178,6 +181,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
       }
     }
   } else if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // =========================== epilogue: TMEM segments -> registers -> C ============================
     const int ew = warp - 4;           // TMEM lane quadrant == warp % 4
     const int row = ew * 32 + lane;    // accumulator row owned by this thread
@@ -197,65 +201,94 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
       const bool accumulate = (d->flags & 1) != 0, skipz = (d->flags & 2) != 0, atomic = (d->flags & 4) != 0;
       for (int64_t mt = sch.m_start; mt < mtiles; mt += sch.m_step) {
         const int64_t m0 = mt * TM;
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[j] = 0.f;
-        for (int sidx = 0; sidx < nseg; ++sidx, ++gseg) {
-          const uint32_t buf = gseg & 1;
-          mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int cb = 0; cb < TN / 16; ++cb) {
-            float hh[16], xx[16];
-            tmem_ld16(tmem + ((uint32_t)(ew * 32) << 16) + buf * 256 + cb * 16, hh);
-            tmem_ld16(tmem + ((uint32_t)(ew * 32) << 16) + buf * 256 + 128 + cb * 16, xx);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += hh[j] + xx[j];
-          }
-          tc_fence_before();
-          mbar_arrive(&S.acc_empty[buf]);
-        }
         float rs = 1.0f;
         if (d->rs_off >= 0) {
           const int64_t m = m0 + row;
           rs = (m < M) ? __ldg(rs_base + d->rs_off * rs_ld + m) : 0.f;
         }
+        const uint32_t tlane = tmem + ((uint32_t)(ew * 32) << 16);
         float4* st = reinterpret_cast<float4*>(S.stage[ew]);
+        // 32 summed + scaled values of my row -> swizzled staging tile -> full 128-byte row segments of C
+        auto emit = [&](int cb, const float* v) {
+          const int rl = lane;
 #pragma unroll
-        for (int cb = 0; cb < TN / 32; ++cb) {
-          if (cb * 32 < ncols) {
-            const int rl = lane;
+          for (int u = 0; u < 8; ++u)
+            st[rl * 8 + (u ^ (rl & 7))] = make_float4(v[4 * u] * rs, v[4 * u + 1] * rs, v[4 * u + 2] * rs, v[4 * u + 3] * rs);
+          __syncwarp();
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              st[rl * 8 + (u ^ (rl & 7))] = make_float4(acc[cb * 32 + 4 * u] * rs, acc[cb * 32 + 4 * u + 1] * rs,
-                                                        acc[cb * 32 + 4 * u + 2] * rs, acc[cb * 32 + 4 * u + 3] * rs);
-            __syncwarp();
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-              const int rr = p * 4 + (lane >> 3), u = lane & 7;
-              const int64_t m = m0 + ew * 32 + rr;
-              const int col = cb * 32 + u * 4;
-              const float rsr = __shfl_sync(0xffffffffu, rs, rr);
-              if (m < M && col < ncols && !(skipz && rsr == 0.f)) {
-                float4 val = st[rr * 8 + (u ^ (rr & 7))];
-                float4* dst = reinterpret_cast<float4*>(C + m * ldc + col);
-                if (atomic) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
-                               "f"(val.z), "f"(val.w) : "memory");
-                } else {
-                  if (accumulate) {
-                    const float4 old = *dst;
-                    val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-                  }
-                  *dst = val;
+          for (int p = 0; p < 8; ++p) {
+            const int rr = p * 4 + (lane >> 3), u = lane & 7;
+            const int64_t m = m0 + ew * 32 + rr;
+            const int col = cb * 32 + u * 4;
+            const float rsr = __shfl_sync(0xffffffffu, rs, rr);
+            if (m < M && col < ncols && !(skipz && rsr == 0.f)) {
+              float4 val = st[rr * 8 + (u ^ (rr & 7))];
+              float4* dst = reinterpret_cast<float4*>(C + m * ldc + col);
+              if (atomic) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
+                             "f"(val.z), "f"(val.w) : "memory");
+              } else {
+                if (accumulate) {
+                  const float4 old = *dst;
+                  val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
                 }
+                *dst = val;
               }
             }
-            __syncwarp();
           }
+          __syncwarp();
+        };
+        if (nseg == 1) {
+          // K <= 320: TMEM -> staging -> C directly, 32 columns at a time
+          const uint32_t buf = gseg & 1;
+          mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int cb = 0; cb < TN / 32; ++cb) {
+            float hh[32], xx[32];
+            const bool need = cb * 32 < ncols;
+            if (need) tmem_ld32x2(tlane + buf * 256 + cb * 32, tlane + buf * 256 + 128 + cb * 32, hh, xx);
+            if (cb == TN / 32 - 1 || (cb + 1) * 32 >= ncols) {
+              if (cb == TN / 32 - 1 || ((cb + 1) * 32 >= ncols && cb * 32 < ncols)) {
+                tc_fence_before();
+                mbar_arrive(&S.acc_empty[buf]);  // every needed column has been read
+              }
+            }
+            if (need) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) hh[j] += xx[j];
+              emit(cb, hh);
+            }
+          }
+          ++gseg;
+        } else {
+          // long reductions: drain each segment into registers (round-to-nearest partial sums)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+          for (int sidx = 0; sidx < nseg; ++sidx, ++gseg) {
+            const uint32_t buf = gseg & 1;
+            mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int cb = 0; cb < TN / 32; ++cb) {
+              float hh[32], xx[32];
+              tmem_ld32x2(tlane + buf * 256 + cb * 32, tlane + buf * 256 + 128 + cb * 32, hh, xx);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[cb * 32 + j] += hh[j] + xx[j];
+            }
+            tc_fence_before();
+            mbar_arrive(&S.acc_empty[buf]);
+          }
+#pragma unroll
+          for (int cb = 0; cb < TN / 32; ++cb)
+            if (cb * 32 < ncols) emit(cb, acc + cb * 32);
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  }
+  if (warp == 8) {
     // =========================== weight-chunk loader ===================================================
     if (lane == 0) {
       uint32_t bcount[BSLOTS] = {0, 0, 0, 0};  // loads issued per slot
@@ -282,7 +315,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
         }
       }
     }
-  } else {
+  } else if (warp == 9) {
     // =========================== MMA issuer ============================================================
     if (lane == 0) {
       constexpr uint32_t SBO = (KC / 4) * 128, LBO = 128;
@@ -419,7 +452,7 @@ extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_tot
   }
   const int64_t nwork = ((M + TM - 1) / TM) * (int64_t)ntiles_total;
   const int grid = (int)(nwork < gemm_sm_count() ? nwork : gemm_sm_count());
-  k_gemm3x<<<grid, 320, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, a_base,
+  k_gemm3x<<<grid, 384, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, a_base,
                                                                  prepared_base, c_base, rowscale_base, rs_ld, M);
   nqb_count_launch();
   cudaError_t e = cudaGetLastError();

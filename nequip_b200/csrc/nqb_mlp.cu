@@ -369,6 +369,88 @@ k_mlp_bwd(const float* __restrict__ emb, const float* __restrict__ W1s, const fl
   if (warp == 4) tmem_dealloc(tmem, 128);
 }
 
+// ---------------------------------------------------------------------------------------------
+// first radial layer on CUDA cores (K = 8): h = silu(emb @ W1s)  and its backward
+//   gemb[e, k] = sum_m gh[e, m] * silu'(pre[e, m]) * W1s[k, m],  pre recomputed from emb
+// (feeds / follows the grouped tensor-core GEMM of the second layer, nqb_gemm.cu)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hidden_fwd(const float* __restrict__ emb, const float* __restrict__ W1s,
+                                                    int64_t E, float* __restrict__ h) {
+  __shared__ float w1[NB * H];
+  for (int i = threadIdx.x; i < NB * H; i += blockDim.x) w1[i] = W1s[i];
+  __syncthreads();
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 4 hidden units of one edge
+  const int64_t e = gid >> 5;
+  const int m0 = (int)(gid & 31) * 4;
+  if (e >= E) return;
+  float x[NB];
+  const float4 x0 = __ldg(reinterpret_cast<const float4*>(emb + e * NB));
+  const float4 x1 = __ldg(reinterpret_cast<const float4*>(emb + e * NB + 4));
+  x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+  float o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float p = 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) p = fmaf(x[k], w1[k * H + m0 + q], p);
+    o[q] = silu_f(p);
+  }
+  *reinterpret_cast<float4*>(h + e * H + m0) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256) k_hidden_bwd(const float* __restrict__ emb, const float* __restrict__ W1s,
+                                                    const float* __restrict__ gh, int64_t E, float* __restrict__ gemb) {
+  __shared__ float w1[NB * H];
+  for (int i = threadIdx.x; i < NB * H; i += blockDim.x) w1[i] = W1s[i];
+  __syncthreads();
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // warp = one edge, lane = 4 hidden units
+  const int64_t e = gid >> 5;
+  const int lane = threadIdx.x & 31, m0 = lane * 4;
+  if (e >= E) return;  // whole warp exits together (E is tested per warp)
+  float x[NB];
+  const float4 x0 = __ldg(reinterpret_cast<const float4*>(emb + e * NB));
+  const float4 x1 = __ldg(reinterpret_cast<const float4*>(emb + e * NB + 4));
+  x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gh + e * H + m0));
+  const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+  float acc[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float p = 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) p = fmaf(x[k], w1[k * H + m0 + q], p);
+    const float sg = 1.0f / (1.0f + expf(-p));
+    const float gp = g[q] * (sg * (1.0f + p * (1.0f - sg)));
+#pragma unroll
+    for (int k = 0; k < NB; ++k) acc[k] = fmaf(gp, w1[k * H + m0 + q], acc[k]);
+  }
+  // reduce the 8 partial sums over the 32 lanes (halving butterfly: 4 + 2 + 1 + 2 shuffles)
+#pragma unroll
+  for (int o = 16, c = NB; o >= 1; o >>= 1) {
+    if (c > 1) {
+      c >>= 1;
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < c) {
+          const float mine = up ? acc[j + c] : acc[j];
+          const float theirs = up ? acc[j] : acc[j + c];
+          acc[j] = mine + __shfl_xor_sync(0xffffffffu, theirs, o);
+        }
+      }
+    } else {
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+    }
+  }
+  // after the three halving steps lane bits (16, 8, 4) select the component: k = 4*b16 + 2*b8 + b4
+  if ((lane & 3) == 0) {
+    const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    gemb[e * NB + k] = acc[0];
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -443,6 +525,34 @@ extern "C" int nqb_mlp_bwd(const float* emb, const float* W1s, const float* prep
   int64_t tiles = (E + TILE_M - 1) / TILE_M;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   k_mlp_bwd<<<grid, 192, sizeof(BwdSmem) + 1024, (cudaStream_t)st>>>(emb, W1s, prep_bwd, grad_w, E, W, grad_emb);
+  nqb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int nqb_mlp_hidden_fwd(const float* emb, const float* W1s, int64_t E, int num_bessel, int hidden, float* h,
+                                  nqb_stream_t st) {
+  if (num_bessel != NB || hidden != H) return nqb_set_error("nqb_mlp_hidden_fwd: only num_bessel=8, hidden=128 is built");
+  if (E < 0) return nqb_set_error("nqb_mlp_hidden_fwd: negative size");
+  if (E == 0) return 0;
+  if (!emb || !W1s || !h) return nqb_set_error("nqb_mlp_hidden_fwd: null pointer");
+  const int64_t threads = E * 32;
+  k_hidden_fwd<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)st>>>(emb, W1s, E, h);
+  nqb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const float* grad_h, int64_t E, int num_bessel,
+                                  int hidden, float* grad_emb, nqb_stream_t st) {
+  if (num_bessel != NB || hidden != H) return nqb_set_error("nqb_mlp_hidden_bwd: only num_bessel=8, hidden=128 is built");
+  if (E < 0) return nqb_set_error("nqb_mlp_hidden_bwd: negative size");
+  if (E == 0) return 0;
+  if (!emb || !W1s || !grad_h || !grad_emb) return nqb_set_error("nqb_mlp_hidden_bwd: null pointer");
+  const int64_t threads = E * 32;
+  k_hidden_bwd<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)st>>>(emb, W1s, grad_h, E, grad_emb);
   nqb_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));

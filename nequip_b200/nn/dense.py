@@ -141,22 +141,31 @@ class SelfConnectionGemm:
 class _RadialMLPGemmFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb, w1s, fwd: ops.GroupedGemm, bwd: ops.GroupedGemm, W: int):
-        E = emb.shape[0]
-        pre = torch.mm(emb, w1s)  # K = 8: not worth a tensor-core pass
-        h = torch.nn.functional.silu(pre)
+        E, hid = emb.shape[0], w1s.shape[1]
+        fast = emb.shape[1] == 8 and hid == 128  # fused CUDA-core kernels for the K = 8 layer
+        if fast:
+            h = torch.empty((E, hid), dtype=emb.dtype, device=emb.device)
+            ops.mlp_hidden_fwd(emb, w1s, h)
+        else:
+            h = torch.nn.functional.silu(torch.mm(emb, w1s))
         out = torch.empty((E, W), dtype=emb.dtype, device=emb.device)
         fwd.run(h, out, E)
-        ctx.bwd, ctx.w1s = bwd, w1s
-        ctx.save_for_backward(pre)
+        ctx.bwd, ctx.w1s, ctx.fast = bwd, w1s, fast
+        ctx.save_for_backward(emb)  # the pre-activation is recomputed in the backward (8 FMAs per value)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gw):
-        (pre,) = ctx.saved_tensors
-        E = pre.shape[0]
-        gh = torch.empty_like(pre)
+        (emb,) = ctx.saved_tensors
+        E, hid = emb.shape[0], ctx.w1s.shape[1]
+        gh = torch.empty((E, hid), dtype=emb.dtype, device=emb.device)
         ctx.bwd.run(gw.contiguous(), gh, E)
+        if ctx.fast:
+            gemb = torch.empty_like(emb)
+            ops.mlp_hidden_bwd(emb, ctx.w1s, gh, gemb)
+            return gemb, None, None, None, None
+        pre = torch.mm(emb, ctx.w1s)
         gpre = torch.ops.aten.silu_backward(gh, pre)
         return torch.mm(gpre, ctx.w1s.t()), None, None, None, None
 

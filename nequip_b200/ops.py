@@ -450,3 +450,17 @@ class GroupedGemm:
             "nqb_gemm_grouped",
         )
         return c
+
+
+def mlp_hidden_fwd(emb: torch.Tensor, w1s: torch.Tensor, h: torch.Tensor) -> None:
+    """``h = silu(emb @ w1s)`` ([E,8] x [8,128])."""
+    _require_cuda(emb, w1s, h)
+    _capi.check(_capi.lib().nqb_mlp_hidden_fwd(_ptr(emb), _ptr(w1s), emb.shape[0], emb.shape[1], w1s.shape[1], _ptr(h),
+                                               _stream()), "nqb_mlp_hidden_fwd")
+
+
+def mlp_hidden_bwd(emb: torch.Tensor, w1s: torch.Tensor, gh: torch.Tensor, gemb: torch.Tensor) -> None:
+    """``gemb = (gh * silu'(emb @ w1s)) @ w1s^T``."""
+    _require_cuda(emb, w1s, gh, gemb)
+    _capi.check(_capi.lib().nqb_mlp_hidden_bwd(_ptr(emb), _ptr(w1s), _ptr(gh), emb.shape[0], emb.shape[1], w1s.shape[1],
+                                               _ptr(gemb), _stream()), "nqb_mlp_hidden_bwd")

@@ -9,6 +9,13 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    # the CPU oracle is what the GPU tests wait for: a sane thread count beats 128-way oversubscription
+    try:
+        import torch
+
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+    except Exception:
+        pass
     config.addinivalue_line("markers", "gpu: test needs a CUDA (sm_100a) device")
 
 

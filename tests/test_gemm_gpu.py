@@ -75,3 +75,22 @@ def test_row_masked_disjoint_writers_accumulate_onto_base():
     gg.run(X.cuda(), out, M, rowscale=onehot_t.cuda())
     ref = base.double() + torch.stack([X[m].double() @ Ws[int(types[m])].double() for m in range(M)])
     assert (out.cpu().double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("E", [1, 33, 1000, 70001])
+def test_mlp_hidden_layer_kernels(E):
+    """First radial layer (K = 8) forward/backward on CUDA cores vs float64 (nequip/nn/mlp.py:262-268)."""
+    g = torch.Generator().manual_seed(E)
+    emb = torch.rand(E, 8, generator=g) * 2 - 0.5
+    w1s = (torch.rand(8, 128, generator=g) * 2 - 1) * 0.6
+    gh = torch.randn(E, 128, generator=g)
+    e_r = emb.double().requires_grad_(True)
+    h_ref = torch.nn.functional.silu(e_r @ w1s.double())
+    (ge_ref,) = torch.autograd.grad(h_ref, e_r, gh.double())
+    h = torch.empty(E, 128, device="cuda")
+    ops.mlp_hidden_fwd(emb.cuda(), w1s.cuda(), h)
+    ge = torch.empty(E, 8, device="cuda")
+    ops.mlp_hidden_bwd(emb.cuda(), w1s.cuda(), gh.cuda(), ge)
+    torch.testing.assert_close(h.cpu().double(), h_ref.detach(), atol=2e-6, rtol=2e-6)
+    torch.testing.assert_close(ge.cpu().double(), ge_ref, atol=2e-5, rtol=2e-5)
