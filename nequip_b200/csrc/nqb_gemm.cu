@@ -248,11 +248,9 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
             float hh[32], xx[32];
             const bool need = cb * 32 < ncols;
             if (need) tmem_ld32x2(tlane + buf * 256 + cb * 32, tlane + buf * 256 + 128 + cb * 32, hh, xx);
-            if (cb == TN / 32 - 1 || (cb + 1) * 32 >= ncols) {
-              if (cb == TN / 32 - 1 || ((cb + 1) * 32 >= ncols && cb * 32 < ncols)) {
-                tc_fence_before();
-                mbar_arrive(&S.acc_empty[buf]);  // every needed column has been read
-              }
+            if (cb == (ncols + 31) / 32 - 1) {  // exactly once per tile: every needed column has been read
+              tc_fence_before();
+              mbar_arrive(&S.acc_empty[buf]);
             }
             if (need) {
 #pragma unroll

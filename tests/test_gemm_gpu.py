@@ -94,3 +94,20 @@ def test_mlp_hidden_layer_kernels(E):
     ops.mlp_hidden_bwd(emb.cuda(), w1s.cuda(), gh.cuda(), ge)
     torch.testing.assert_close(h.cpu().double(), h_ref.detach(), atol=2e-6, rtol=2e-6)
     torch.testing.assert_close(ge.cpu().double(), ge_ref, atol=2e-5, rtol=2e-5)
+
+
+@pytest.mark.timeout(120)
+def test_persistent_many_tiles_ragged_n():
+    """More work items than CTAs (persistent loops reuse the TMEM accumulators and barriers many times) with a
+    ragged last N-tile (192 = 128 + 64 columns) -- guards the once-per-tile accumulator hand-back."""
+    g = torch.Generator().manual_seed(11)
+    M, K, N = 148 * 128 * 3 + 77, 128, 192
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    gg = ops.GroupedGemm([ops.GemmProblem(0, K, 0, N, B)], "cuda")
+    C = torch.empty(M, N, device="cuda")
+    for _ in range(3):
+        gg.run(A.cuda(), C, M)
+    torch.cuda.synchronize()
+    ref = A[-5000:].double() @ B.double()
+    assert (C[-5000:].cpu().double() - ref).abs().max().item() <= 1.5e-6 * ref.abs().max().item()
