@@ -67,7 +67,8 @@ def ensure_runtime(force: bool = False) -> str:
         if force or _newer(srcs, out):
             os.makedirs(LIBDIR, exist_ok=True)
             tmp = out + f".tmp{os.getpid()}"
-            _run([nvcc_path(), *ARCH_FLAGS, *COMMON_FLAGS, "-I", INCLUDE, "-Xptxas", "-v", "-o", tmp, *cus, "-ldl"])
+            extra = os.environ.get("NQB_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DNQB_GEMM_PROF (tools/bench_gemm.py --prof)
+            _run([nvcc_path(), *ARCH_FLAGS, *COMMON_FLAGS, *extra, "-I", INCLUDE, "-Xptxas", "-v", "-o", tmp, *cus, "-ldl"])
             os.replace(tmp, out)
     return out
 

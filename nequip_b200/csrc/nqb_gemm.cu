@@ -15,23 +15,41 @@
 // step), so the two cross terms go to their own TMEM accumulator and long reductions are cut into
 // segments of SEG_CHUNKS*32 in K whose partial sums are added in registers (round-to-nearest).
 //
-// Roles per CTA (384 threads = 3 warpgroups with setmaxnreg-rebalanced registers, persistent over (M-tile, N-tile) work items, N-tile fastest so that
-// the CTAs working on one A tile run together and share it in L2):
-//   warps 0-3  producers: stream the A chunk [128 x 32] through registers (coalesced 16-byte loads, one
-//              chunk ahead, across work-item boundaries), split hi/lo into the canonical K-major
-//              core-matrix layout in shared memory
-//   warps 4-7  epilogue: drain finished accumulator segments TMEM -> registers (fp32 adds), then write C
-//              through a swizzled staging tile so that the global stores are full 128-byte rows;
-//              overlaps with the production / MMA of the next work item (TMEM is double buffered)
-//   warp  8    lane 0: cp.async.bulk of the pre-split weight chunk (+ mbarrier complete_tx)
-//   warp  9    lane 0: tcgen05.mma M=128, N<=128, K=8: 4 k-steps x 3 terms per chunk; tcgen05.commit
+// Roles per CTA (384 threads = 3 warpgroups with setmaxnreg-rebalanced registers, persistent over
+// (M-tile, N-tile) work items; the CTAs working on one A tile run together and share it in L2):
+//   warps 0-3   producers: stream the A chunk [128 x 32] through registers (coalesced 16-byte loads,
+//               THREE chunks ahead across work-item boundaries = 48 KB in flight per SM: with one chunk
+//               ahead the role was L2-latency bound at ~2600 cycles per chunk, profiles/r01_gemm_roles.txt),
+//               split hi/lo into the canonical K-major core-matrix layout in shared memory
+//   warps 4-7   epilogue: drain finished accumulator segments TMEM -> registers (fp32 adds), then write C
+//               through a swizzled staging tile so that the global stores are full 128-byte rows;
+//               overlaps with the production / MMA of the next work item (TMEM is double buffered)
+//   warp  8     lane 0: cp.async.bulk of the pre-split weight chunk (+ mbarrier complete_tx)
+//   warp  9     tcgen05.mma M=128, N<=128, K=8: 4 k-steps x 3 terms per chunk; tcgen05.commit
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "../../include/nqb.h"
 #include "nqb_tc.cuh"
 
 namespace {
+
+// Per-role stall accounting (tools/bench_gemm.py --prof, build with -DNQB_GEMM_PROF): cycles CTA 0's
+// lane 0 of each role spends in each mbarrier wait, and the role's total.
+#ifdef NQB_GEMM_PROF
+__device__ unsigned long long g_prof[16];
+#define PROF_DECL long long pw_[4] = {0, 0, 0, 0}; const long long pt0_ = clock64();
+#define PROF_WAIT(i, stmt) { const long long t_ = clock64(); stmt; pw_[i] += clock64() - t_; }
+#define PROF_END(base) { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { \
+    for (int i_ = 0; i_ < 3; ++i_) g_prof[(base) + i_] = (unsigned long long)pw_[i_]; \
+    g_prof[(base) + 3] = (unsigned long long)(clock64() - pt0_); } }
+#else
+#define PROF_DECL
+#define PROF_WAIT(i, stmt) { stmt; }
+#define PROF_END(base) {}
+#endif
 
 constexpr int TM = 128;          // rows per tile
 constexpr int TN = 128;          // max columns per tile
@@ -39,6 +57,11 @@ constexpr int KC = 32;           // K chunk
 constexpr int ASTAGES = 2;       // A ring (the producers hold one more chunk in registers)
 constexpr int BSLOTS = 4;        // B slots: a ring when K > 128, resident per N-tile when K <= 128
 constexpr int SEG_CHUNKS = 10;   // chunks per accumulation segment (40 accumulate steps on the hi*hi accumulator)
+constexpr int NPW = 4;            // producer warps
+constexpr int NPROD = NPW * 32;   // producer threads
+constexpr int NTHREADS = NPROD + 256;  // + epilogue warpgroup + {loader, MMA, 2 idle} warps
+constexpr int RG = TM / NPW / 8;  // 8-row groups per producer warp
+constexpr int PF = 3;            // A chunks in flight in registers per producer thread
 constexpr int BLOCK_FLOATS = 2 * TN * KC;  // one prepared weight block: [hi | lo] x [128 x 32]
 
 struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
@@ -100,7 +123,7 @@ __device__ __forceinline__ void decode_q(const GemmDesc* descs, int ndesc, int q
   w.resident = w.kchunks <= BSLOTS;
 }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const float* __restrict__ a_base,
          const float* __restrict__ b_base, float* __restrict__ c_base, const float* __restrict__ rs_base, int64_t rs_ld,
          int64_t M) {
@@ -110,12 +133,12 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   const int64_t mtiles = (M + TM - 1) / TM;
 
   if (tid == 0) {
-    for (int s = 0; s < ASTAGES; ++s) { mbar_init(&S.a_full[s], 128); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < ASTAGES; ++s) { mbar_init(&S.a_full[s], NPROD); mbar_init(&S.a_empty[s], 1); }
     for (int s = 0; s < BSLOTS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 128); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&S.tmem_base, 512);
+  if (warp == NPW + 4) tmem_alloc(&S.tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -123,48 +146,72 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   const Sched sch(blockIdx.x, gridDim.x, ntiles_total);
 
   // register budget per warpgroup (launch: 65536 / 384 = 168 each): the epilogue keeps a 128-value row of
-  // partial sums in registers, the producers and the two single-lane roles need few
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    // =========================== A producer: global -> registers (one chunk ahead) -> split -> smem ======
+  // partial sums in registers (232), the producers hold PF + 1 chunks (168), loader and MMA warps need few (56)
+  if (warp < NPW) {
+    // =========================== A producer: global -> registers (PF chunks ahead) -> split -> smem ======
+    // thread -> rows warp*(8 RG) + g*8 + r8 (g < RG), k-groups hp*4 + kq (hp = 0, 1): 2 RG x 16 bytes per chunk
     const int r8 = lane & 7, kq = lane >> 3;
-    uint32_t it = 0;
-    float4 v[8], vn[8];
-    for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
+    PROF_DECL
+    // prefetch cursor over the CTA's flat sequence of (N-tile q, M-tile mt, chunk c)
+    int pq = sch.q, pc = 0, pkch = 1, pK = 0;
+    int64_t pmt = sch.m_start, plda = 0;
+    const float* pA = nullptr;
+    bool pvalid = pq < sch.nq_total && sch.m_start < mtiles;
+    auto open_q = [&]() {
       WorkQ w;
-      decode_q(descs, ndesc, q, w);
-      const float* A = a_base + w.d->a_off;
-      const int64_t lda = w.d->lda;
-      auto load_chunk = [&](int64_t mt, int c, float4* dst) {
+      decode_q(descs, ndesc, pq, w);
+      pA = a_base + w.d->a_off;
+      plda = w.d->lda;
+      pkch = w.kchunks;
+      pK = w.K;
+    };
+    if (pvalid) open_q();
+    auto fetch = [&](float4* dst) {  // load the cursor's chunk (if any) and advance
+      if (pvalid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int64_t m = mt * TM + warp * 32 + g * 8 + r8;
+        for (int g = 0; g < RG; ++g) {
+          const int64_t m = pmt * TM + warp * (8 * RG) + g * 8 + r8;
 #pragma unroll
           for (int hp = 0; hp < 2; ++hp) {
-            const int k = c * KC + (hp * 4 + kq) * 4;
-            dst[g * 2 + hp] = (m < M && k < w.K) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + k))
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int k = pc * KC + (hp * 4 + kq) * 4;
+            dst[g * 2 + hp] = (m < M && k < pK) ? ldg_stream(pA + m * plda + k) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-      };
-      int64_t mt = sch.m_start;
-      int c = 0;
-      if (mt < mtiles) load_chunk(mt, 0, v);
-      while (mt < mtiles) {
-        int cn = c + 1;
-        int64_t mtn = mt;
-        if (cn == w.kchunks) { cn = 0; mtn = mt + sch.m_step; }
-        if (mtn < mtiles) load_chunk(mtn, cn, vn);
+        if (++pc == pkch) {
+          pc = 0;
+          pmt += sch.m_step;
+          if (pmt >= mtiles) {
+            pmt = sch.m_start;
+            pq += sch.q_step;
+            pvalid = pq < sch.nq_total;
+            if (pvalid) open_q();
+          }
+        }
+      }
+    };
+    float4 v[PF + 1][2 * RG];
+    bool ok[PF + 1];
+#pragma unroll
+    for (int p = 0; p < PF; ++p) { ok[p] = pvalid; fetch(v[p]); }
+    uint32_t it = 0;
+    bool done = false;
+    while (!done) {
+#pragma unroll
+      for (int p = 0; p <= PF; ++p) {
+        if (done) break;
+        ok[(p + PF) % (PF + 1)] = pvalid;
+        PROF_WAIT(1, fetch(v[(p + PF) % (PF + 1)]))
+        if (!ok[p]) { done = true; break; }
         const uint32_t s = it % ASTAGES, ph = (it / ASTAGES) & 1;
-        if (it >= ASTAGES) mbar_wait(&S.a_empty[s], ph ^ 1);
+        if (it >= ASTAGES) PROF_WAIT(0, mbar_wait(&S.a_empty[s], ph ^ 1))
         float* ahi = S.a[s];
         float* alo = S.a[s] + TM * KC;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < RG; ++g) {
 #pragma unroll
           for (int hp = 0; hp < 2; ++hp) {
-            const int r = warp * 32 + g * 8 + r8, kg = hp * 4 + kq;
-            const float4 a = v[g * 2 + hp];
+            const int r = warp * (8 * RG) + g * 8 + r8, kg = hp * 4 + kq;
+            const float4 a = v[p][g * 2 + hp];
             const float4 hi = make_float4(tf32_rn(a.x), tf32_rn(a.y), tf32_rn(a.z), tf32_rn(a.w));
             const float4 lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
             const int off = (r >> 3) * (KC / 4 * 32) + kg * 32 + (r & 7) * 4;
@@ -172,21 +219,19 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
             *reinterpret_cast<float4*>(alo + off) = lo;
           }
         }
-        fence_proxy_async();
-        mbar_arrive(&S.a_full[s]);
+        PROF_WAIT(2, fence_proxy_async(); mbar_arrive(&S.a_full[s]))
         ++it;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = vn[j];
-        c = cn; mt = mtn;
       }
     }
-  } else if (warp < 8) {
+    if (warp == 0) PROF_END(0)
+  } else if (warp < NPW + 4) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // =========================== epilogue: TMEM segments -> registers -> C ============================
-    const int ew = warp - 4;           // TMEM lane quadrant == warp % 4
+    const int ew = warp - NPW;         // TMEM lane quadrant == warp % 4
     const int row = ew * 32 + lane;    // accumulator row owned by this thread
     uint32_t gseg = 0;
     float acc[TN];
+    PROF_DECL
     for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
       WorkQ w;
       decode_q(descs, ndesc, q, w);
@@ -198,7 +243,8 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
       // flags: bit0 read-modify-write accumulate (single writer per element within the launch),
       //        bit1 rows whose row scale is zero are not touched (disjoint row-masked writers),
       //        bit2 accumulate with red.global.add (several problems of this launch add into the same C)
-      const bool accumulate = (d->flags & 1) != 0, skipz = (d->flags & 2) != 0, atomic = (d->flags & 4) != 0;
+      // both accumulate modes add with red.global (performed at L2)
+      const bool reduce = (d->flags & 5) != 0, skipz = (d->flags & 2) != 0;
       for (int64_t mt = sch.m_start; mt < mtiles; mt += sch.m_step) {
         const int64_t m0 = mt * TM;
         float rs = 1.0f;
@@ -207,33 +253,37 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
           rs = (m < M) ? __ldg(rs_base + d->rs_off * rs_ld + m) : 0.f;
         }
         const uint32_t tlane = tmem + ((uint32_t)(ew * 32) << 16);
-        float4* st = reinterpret_cast<float4*>(S.stage[ew]);
         // 32 summed + scaled values of my row -> swizzled staging tile -> full 128-byte row segments of C
-        auto emit = [&](int cb, const float* v) {
-          const int rl = lane;
+        // (lane -> row p*4 + lane/8, 16-byte column group lane%8).  Everything that does not depend on p is
+        // hoisted: a branchy first version of this block cost ~2000 cycles per call and bound the K = 128
+        // problems (profiles/r01_gemm_roles.txt).
+        float4* st = reinterpret_cast<float4*>(S.stage[ew]);
+        const int sub = lane >> 3, u = lane & 7;
+        const uint32_t rowmask = __ballot_sync(0xffffffffu, (m0 + row < M) && !(skipz && rs == 0.f));
+        float* c_lane = C + (m0 + ew * 32 + sub) * ldc + u * 4;  // row `sub` of this warp's 32, column group u
+        const int64_t pstep = 4 * ldc;
+        // MODE 0: plain stores, 1: reduce-adds, 2: decided at run time (one short branch per store)
+        auto emit = [&](auto mode_tag, int cb, const float* v) {
+          constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            st[rl * 8 + (u ^ (rl & 7))] = make_float4(v[4 * u] * rs, v[4 * u + 1] * rs, v[4 * u + 2] * rs, v[4 * u + 3] * rs);
+          for (int k = 0; k < 8; ++k)
+            st[lane * 8 + (k ^ (lane & 7))] = make_float4(v[4 * k] * rs, v[4 * k + 1] * rs, v[4 * k + 2] * rs, v[4 * k + 3] * rs);
           __syncwarp();
+          const bool colok = cb * 32 + u * 4 < ncols;
+          float* dst = c_lane + cb * 32;
+          float4 val[8];
+#pragma unroll
+          for (int p = 0; p < 8; ++p) val[p] = st[(p * 4 + sub) * 8 + (u ^ ((p * 4 + sub) & 7))];
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
-            const int rr = p * 4 + (lane >> 3), u = lane & 7;
-            const int64_t m = m0 + ew * 32 + rr;
-            const int col = cb * 32 + u * 4;
-            const float rsr = __shfl_sync(0xffffffffu, rs, rr);
-            if (m < M && col < ncols && !(skipz && rsr == 0.f)) {
-              float4 val = st[rr * 8 + (u ^ (rr & 7))];
-              float4* dst = reinterpret_cast<float4*>(C + m * ldc + col);
-              if (atomic) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
-                             "f"(val.z), "f"(val.w) : "memory");
-              } else {
-                if (accumulate) {
-                  const float4 old = *dst;
-                  val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-                }
-                *dst = val;
-              }
+            const bool ok = colok && ((rowmask >> (p * 4 + sub)) & 1u);
+            float* d4 = dst + p * pstep;
+            if (ok) {
+              if (MODE == 1 || (MODE == 2 && reduce))
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4), "f"(val[p].x), "f"(val[p].y),
+                             "f"(val[p].z), "f"(val[p].w) : "memory");
+              else
+                *reinterpret_cast<float4*>(d4) = val[p];
             }
           }
           __syncwarp();
@@ -241,22 +291,21 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
         if (nseg == 1) {
           // K <= 320: TMEM -> staging -> C directly, 32 columns at a time
           const uint32_t buf = gseg & 1;
-          mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1);
+          PROF_WAIT(0, mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1))
           tc_fence_after();
-#pragma unroll
-          for (int cb = 0; cb < TN / 32; ++cb) {
+          const int ncb = (ncols + 31) / 32;
+#pragma unroll 1
+          for (int cb = 0; cb < ncb; ++cb) {
             float hh[32], xx[32];
-            const bool need = cb * 32 < ncols;
-            if (need) tmem_ld32x2(tlane + buf * 256 + cb * 32, tlane + buf * 256 + 128 + cb * 32, hh, xx);
-            if (cb == (ncols + 31) / 32 - 1) {  // exactly once per tile: every needed column has been read
+            PROF_WAIT(1, tmem_ld32x2(tlane + buf * 256 + cb * 32, tlane + buf * 256 + 128 + cb * 32, hh, xx))
+            if (cb == ncb - 1) {  // exactly once per tile: every needed column has been read
               tc_fence_before();
               mbar_arrive(&S.acc_empty[buf]);
             }
-            if (need) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) hh[j] += xx[j];
-              emit(cb, hh);
-            }
+            for (int j = 0; j < 32; ++j) hh[j] += xx[j];
+            if (reduce) PROF_WAIT(2, emit(std::integral_constant<int, 1>{}, cb, hh))
+            else PROF_WAIT(2, emit(std::integral_constant<int, 0>{}, cb, hh))
           }
           ++gseg;
         } else {
@@ -265,7 +314,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
           for (int j = 0; j < TN; ++j) acc[j] = 0.f;
           for (int sidx = 0; sidx < nseg; ++sidx, ++gseg) {
             const uint32_t buf = gseg & 1;
-            mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1);
+            PROF_WAIT(0, mbar_wait(&S.acc_full[buf], (gseg >> 1) & 1))
             tc_fence_after();
 #pragma unroll
             for (int cb = 0; cb < TN / 32; ++cb) {
@@ -279,24 +328,26 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
           }
 #pragma unroll
           for (int cb = 0; cb < TN / 32; ++cb)
-            if (cb * 32 < ncols) emit(cb, acc + cb * 32);
+            if (cb * 32 < ncols) emit(std::integral_constant<int, 2>{}, cb, acc + cb * 32);
         }
       }
     }
-  } else if (warp >= 8) {
+    if (warp == NPW) PROF_END(4)
+  } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   }
-  if (warp == 8) {
+  if (warp == NPW + 4) {
     // =========================== weight-chunk loader ===================================================
     if (lane == 0) {
-      uint32_t bcount[BSLOTS] = {0, 0, 0, 0};  // loads issued per slot
+      uint32_t bused = 0, bpar = 0;             // per-slot bit: slot loaded before / parity of its load count
       uint32_t bit = 0;                         // ring position (streaming mode)
       auto load_slot = [&](int slot, const float* src, uint32_t bytes) {
-        if (bcount[slot] > 0) mbar_wait(&S.b_empty[slot], (bcount[slot] - 1) & 1);
+        if ((bused >> slot) & 1) mbar_wait(&S.b_empty[slot], ((bpar >> slot) & 1) ^ 1);
         mbar_expect_tx(&S.b_full[slot], 2 * bytes);
         bulk_g2s(S.b[slot], src, bytes, &S.b_full[slot]);
         bulk_g2s(S.b[slot] + TN * KC, src + TN * KC, bytes, &S.b_full[slot]);
-        ++bcount[slot];
+        bused |= 1u << slot;
+        bpar ^= 1u << slot;
       };
       for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
         WorkQ w;
@@ -313,69 +364,84 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == NPW + 5) {
     // =========================== MMA issuer ============================================================
-    if (lane == 0) {
-      constexpr uint32_t SBO = (KC / 4) * 128, LBO = 128;
-      uint32_t it = 0, gseg = 0, bit = 0;
-      uint32_t bcount[BSLOTS] = {0, 0, 0, 0};  // loads consumed (waited for) per slot
-      for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
-        WorkQ w;
-        decode_q(descs, ndesc, q, w);
-        const int nmma = (w.ncols + 15) & ~15;
-        const uint32_t idesc = make_idesc(TM, nmma);
-        bool first_mt = true;
-        for (int64_t mt = sch.m_start; mt < mtiles; mt += sch.m_step) {
-          for (int c0 = 0; c0 < w.kchunks; c0 += SEG_CHUNKS, ++gseg) {
-            const uint32_t buf = gseg & 1;
-            if (gseg >= 2) mbar_wait(&S.acc_empty[buf], ((gseg >> 1) - 1) & 1);
+    // The tensor pipe retires an M128 x N128 x K8 MMA every 64 cycles but one thread issues them, and every
+    // instruction between two tcgen05.mma costs issue latency (tools/microbench/umma.cu: a branchy
+    // 40-instruction body drops the rate to ~250 cycles/MMA).  So: the WHOLE warp runs the (warp-uniform)
+    // loops, which lets the compiler keep descriptors in uniform registers instead of broadcasting them
+    // from lane 0 around each MMA; one elected lane issues; descriptors are built once and advanced by adds.
+    const bool leader = elect_one();
+    constexpr uint32_t SBO = (KC / 4) * 128, LBO = 128;
+    const uint64_t dA0 = make_desc(smem_u32(S.a[0]), LBO, SBO);
+    const uint64_t dB0 = make_desc(smem_u32(S.b[0]), LBO, SBO);
+    constexpr uint64_t A_STAGE = (2 * TM * KC * sizeof(float)) >> 4, A_LO = (TM * KC * sizeof(float)) >> 4;
+    constexpr uint64_t B_SLOT = (BLOCK_FLOATS * sizeof(float)) >> 4, B_LO = (TN * KC * sizeof(float)) >> 4;
+    uint32_t it = 0, gseg = 0, bit = 0;
+    uint32_t bpar = 0;  // per-slot bit: parity of the loads consumed (waited for)
+    PROF_DECL
+    for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
+      WorkQ w;
+      decode_q(descs, ndesc, q, w);
+      const int nmma = (w.ncols + 15) & ~15;
+      const uint32_t idesc = make_idesc(TM, nmma);
+      bool first_mt = true;
+      for (int64_t mt = sch.m_start; mt < mtiles; mt += sch.m_step) {
+        for (int c0 = 0; c0 < w.kchunks; c0 += SEG_CHUNKS, ++gseg) {
+          const uint32_t buf = gseg & 1;
+          if (gseg >= 2) PROF_WAIT(0, mbar_wait(&S.acc_empty[buf], ((gseg >> 1) - 1) & 1))
+          tc_fence_after();
+          const uint32_t d_hh = tmem + buf * 256, d_x = d_hh + 128;
+          uint32_t fresh = 1;  // first chunk of the segment overwrites the accumulators
+          const int c1 = min(w.kchunks, c0 + SEG_CHUNKS);
+          for (int c = c0; c < c1; ++c, ++it) {
+            const uint32_t s = it % ASTAGES, ph = (it / ASTAGES) & 1;
+            uint32_t slot;
+            if (w.resident) {
+              slot = c;
+              if (first_mt) { PROF_WAIT(1, mbar_wait(&S.b_full[slot], (bpar >> slot) & 1)) bpar ^= 1u << slot; }
+            } else {
+              slot = bit % BSLOTS;
+              ++bit;
+              PROF_WAIT(1, mbar_wait(&S.b_full[slot], (bpar >> slot) & 1))
+              bpar ^= 1u << slot;
+            }
+            PROF_WAIT(2, mbar_wait(&S.a_full[s], ph))
             tc_fence_after();
-            const uint32_t d_hh = tmem + buf * 256, d_x = d_hh + 128;
-            uint32_t acc_hh = 0, acc_x = 0;
-            const int c1 = min(w.kchunks, c0 + SEG_CHUNKS);
-            for (int c = c0; c < c1; ++c, ++it) {
-              const uint32_t s = it % ASTAGES, ph = (it / ASTAGES) & 1;
-              int slot;
-              if (w.resident) {
-                slot = c;
-                if (first_mt) { mbar_wait(&S.b_full[slot], bcount[slot] & 1); ++bcount[slot]; }
-              } else {
-                slot = bit % BSLOTS;
-                ++bit;
-                mbar_wait(&S.b_full[slot], bcount[slot] & 1);
-                ++bcount[slot];
-              }
-              mbar_wait(&S.a_full[s], ph);
-              tc_fence_after();
-              const uint32_t a_hi = smem_u32(S.a[s]), a_lo = a_hi + TM * KC * sizeof(float);
-              const uint32_t b_hi = smem_u32(S.b[slot]), b_lo = b_hi + TN * KC * sizeof(float);
+            const uint64_t a_hi = dA0 + (uint64_t)(s * (uint32_t)A_STAGE), a_lo = a_hi + A_LO;
+            const uint64_t b_hi = dB0 + (uint64_t)(slot * (uint32_t)B_SLOT), b_lo = b_hi + B_LO;
+            if (leader) {
+              // k-step advance = 256 bytes = 16 descriptor units
+              umma_tf32(d_hh, a_hi, b_hi, idesc, fresh ^ 1);
+              umma_tf32(d_x, a_lo, b_hi, idesc, fresh ^ 1);
+              umma_tf32_acc(d_x, a_hi, b_lo, idesc);
 #pragma unroll
-              for (int ks = 0; ks < KC / 8; ++ks) {
-                umma_tf32(d_hh, make_desc(a_hi + ks * 256, LBO, SBO), make_desc(b_hi + ks * 256, LBO, SBO), idesc, acc_hh);
-                acc_hh = 1;
-              }
-#pragma unroll
-              for (int ks = 0; ks < KC / 8; ++ks) {
-                umma_tf32(d_x, make_desc(a_lo + ks * 256, LBO, SBO), make_desc(b_hi + ks * 256, LBO, SBO), idesc, acc_x);
-                acc_x = 1;
-                umma_tf32(d_x, make_desc(a_hi + ks * 256, LBO, SBO), make_desc(b_lo + ks * 256, LBO, SBO), idesc, 1);
+              for (int ks = 1; ks < KC / 8; ++ks) {
+                umma_tf32_acc(d_hh, a_hi + ks * 16, b_hi + ks * 16, idesc);
+                umma_tf32_acc(d_x, a_lo + ks * 16, b_hi + ks * 16, idesc);
+                umma_tf32_acc(d_x, a_hi + ks * 16, b_lo + ks * 16, idesc);
               }
               umma_commit(&S.a_empty[s]);
               if (!w.resident) umma_commit(&S.b_empty[slot]);
             }
-            umma_commit(&S.acc_full[buf]);
+            fresh = 0;
+            __syncwarp();
           }
-          first_mt = false;
+          if (leader) umma_commit(&S.acc_full[buf]);
+          __syncwarp();
         }
-        // resident weights: release the slots once every MMA of this N-tile has retired
-        if (w.resident && sch.m_start < mtiles)
-          for (int c = 0; c < w.kchunks; ++c) umma_commit(&S.b_empty[c]);
+        first_mt = false;
       }
+      // resident weights: release the slots once every MMA of this N-tile has retired
+      if (w.resident && sch.m_start < mtiles && leader)
+        for (int c = 0; c < w.kchunks; ++c) umma_commit(&S.b_empty[c]);
+      __syncwarp();
     }
+    PROF_END(8)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == NPW + 4) tmem_dealloc(tmem, 512);
 }
 
 // prepared layout: for n-tile j, k-chunk c: block (j * kchunks + c) of BLOCK_FLOATS floats = [hi | lo],
@@ -403,6 +469,11 @@ __global__ void k_gemm_prepare(const float* __restrict__ B, int64_t ldb, int K, 
 
 extern "C" int nqb_set_error(const char* msg);
 extern "C" void nqb_count_launch(void);
+#ifdef NQB_GEMM_PROF
+extern "C" int nqb_gemm_prof_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 16);
+}
+#endif
 
 static int gemm_sm_count() {
   static int n = 0;

@@ -20,9 +20,14 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
 __global__ void __launch_bounds__(128, 1) k2(long long* out, int nmma, int N, int pattern, int noise) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[4];
   __shared__ uint32_t tbase;
   __shared__ volatile int stop;
-  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) ((float*)sm)[i] = 0.f;
+  const int nonzero = noise & 2, commits = noise & 4;
+  noise &= 1;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x)
+    ((float*)sm)[i] = nonzero ? (float)((i * 2654435761u) >> 8 & 0xffff) * 1.0e-4f - 3.0f : 0.f;
+  if (threadIdx.x == 0) for (int q = 0; q < 4; ++q) mbar_init(&bar2[q], 1);
   if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); stop = 0; }
   if (threadIdx.x < 32) tmem_alloc(&tbase, 512);
   fence_proxy_async();
@@ -40,8 +45,13 @@ __global__ void __launch_bounds__(128, 1) k2(long long* out, int nmma, int N, in
       if (pattern == 0) acc = i & 1;
       else if (pattern == 1) acc = 0;
       else if (pattern == 2) acc = ((i % 12) < 4) ? 0 : 1;
-      else acc = i & 3;
+      else if (pattern == 3) acc = i & 3;
+      else if (pattern == 4) acc = (i & 1) * 2;                       // columns 0 / 256 alternating
+      else if (pattern == 5) acc = ((i % 12) < 4) ? 0 : 2;            // 4x col 0 then 8x col 256
+      else if (pattern == 6) acc = ((i % 3) == 0) ? 0 : 2;            // hh, x, x interleaved, cols 0 / 256
+      else acc = ((i % 3) == 0) ? 0 : 1;                              // hh, x, x interleaved, cols 0 / 128
       umma_tf32(tbase + acc * 128, da, db, idesc, 1);
+      if (commits && (i % 12) == 11) umma_commit(&bar2[(i / 12) & 3]);
     }
     umma_commit(&bar);
     mbar_wait(&bar, 0);
@@ -136,5 +146,14 @@ int main() {
   run2("tf32 N=128 four accumulators round robin", 3, 0, d_out, nsm);
   run2("tf32 N=128 alternating + smem store noise (3 warps)", 0, 1, d_out, nsm);
   run2("tf32 N=128 kernel pattern + smem store noise", 2, 1, d_out, nsm);
+  run2("tf32 N=128 cols 0/256 alternating", 4, 0, d_out, nsm);
+  run2("tf32 N=128 4x col0 then 8x col256", 5, 0, d_out, nsm);
+  run2("tf32 N=128 hh,x,x interleaved cols 0/256", 6, 0, d_out, nsm);
+  run2("tf32 N=128 hh,x,x interleaved cols 0/128", 7, 0, d_out, nsm);
+  run2("tf32 N=128 hh,x,x interleaved cols 0/256 + commits", 6, 4, d_out, nsm);
+  run2("tf32 N=128 kernel pattern, NONZERO operands", 2, 2, d_out, nsm);
+  run2("tf32 N=128 kernel pattern, commit every 12", 2, 4, d_out, nsm);
+  run2("tf32 N=128 kernel pattern, nonzero + commits + noise", 2, 7, d_out, nsm);
+  run2("tf32 N=128 alternating, NONZERO operands", 0, 2, d_out, nsm);
   return 0;
 }
