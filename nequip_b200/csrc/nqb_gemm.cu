@@ -13,7 +13,7 @@
 // fp32 parity on a TF32 pipe: a = hi + lo (hi = cvt.rna.tf32), D = A_hi B_hi + (A_lo B_hi + A_hi B_lo).
 // The tensor core's fp32 accumulate truncates (measured ~3e-8 relative bias per accumulation
 // step), so the two cross terms go to their own TMEM accumulator and long reductions are cut into
-// segments of SEG_CHUNKS*32 in K whose partial sums are added in registers (round-to-nearest).
+// segments of SEG_H*16 = 320 in K whose partial sums are added in registers (round-to-nearest).
 //
 // Roles per CTA (384 threads = 3 warpgroups with setmaxnreg-rebalanced registers, persistent over
 // (M-tile, N-tile) work items; the CTAs working on one A tile run together and share it in L2):
@@ -54,14 +54,17 @@ __device__ unsigned long long g_prof[16];
 constexpr int TM = 128;          // rows per tile
 constexpr int TN = 128;          // max columns per tile
 constexpr int KC = 32;           // K chunk
-constexpr int ASTAGES = 2;       // A ring (the producers hold one more chunk in registers)
+constexpr int KH = 16;           // A is staged in half-chunks of 16 k
+constexpr int RAW = 6;           // ring of raw A half-chunks (8 KB each), filled by cp.async
+constexpr int DEPTH = 4;         // half-chunks in flight per CTA (32 KB)
+constexpr int NLO = 2;           // ring of A low-part half-chunks
 constexpr int BSLOTS = 4;        // B slots: a ring when K > 128, resident per N-tile when K <= 128
-constexpr int SEG_CHUNKS = 10;   // chunks per accumulation segment (40 accumulate steps on the hi*hi accumulator)
+constexpr int SEG_H = 20;        // half-chunks per accumulation segment (40 accumulate steps on the hi*hi accumulator)
 constexpr int NPW = 4;            // producer warps
 constexpr int NPROD = NPW * 32;   // producer threads
 constexpr int NTHREADS = NPROD + 256;  // + epilogue warpgroup + {loader, MMA, 2 idle} warps
 constexpr int RG = TM / NPW / 8;  // 8-row groups per producer warp
-constexpr int PF = 3;            // A chunks in flight in registers per producer thread
+static_assert(DEPTH <= RAW - 2, "a raw stage is refilled two half-chunks after its MMA was issued");
 constexpr int BLOCK_FLOATS = 2 * TN * KC;  // one prepared weight block: [hi | lo] x [128 x 32]
 
 struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
@@ -72,10 +75,11 @@ struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
 };
 
 struct Smem {
-  float a[ASTAGES][2 * TM * KC];   // 2 x 32 KB
+  float araw[RAW][TM * KH];        // 6 x 8 KB: fp32 A half-chunks, canonical K-major core-matrix layout
+  float alo[NLO][TM * KH];         // 2 x 8 KB: their tf32 low parts
   float b[BSLOTS][BLOCK_FLOATS];   // 4 x 32 KB
   float stage[4][32 * 32];         // epilogue staging, one 32x32 tile per warp (swizzled)
-  uint64_t a_full[ASTAGES], a_empty[ASTAGES];
+  uint64_t a_full[RAW], a_done[RAW];
   uint64_t b_full[BSLOTS], b_empty[BSLOTS];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
@@ -111,7 +115,7 @@ struct Sched {
 
 struct WorkQ {  // one N-tile of one problem
   const GemmDesc* d;
-  int nt, kchunks, K, ncols;
+  int nt, kchunks, nh, K, ncols;  // kchunks: weight chunks of 32 k; nh: A half-chunks of 16 k
   bool resident;
 };
 __device__ __forceinline__ void decode_q(const GemmDesc* descs, int ndesc, int q, WorkQ& w) {
@@ -119,6 +123,7 @@ __device__ __forceinline__ void decode_q(const GemmDesc* descs, int ndesc, int q
   w.nt = q - (int)w.d->tile0;
   w.kchunks = (int)w.d->kchunks;
   w.K = (int)w.d->K;
+  w.nh = (w.K + KH - 1) / KH;
   w.ncols = min(TN, (int)w.d->N - w.nt * TN);
   w.resident = w.kchunks <= BSLOTS;
 }
@@ -133,7 +138,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   const int64_t mtiles = (M + TM - 1) / TM;
 
   if (tid == 0) {
-    for (int s = 0; s < ASTAGES; ++s) { mbar_init(&S.a_full[s], NPROD); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < RAW; ++s) { mbar_init(&S.a_full[s], NPROD); mbar_init(&S.a_done[s], 1); }
     for (int s = 0; s < BSLOTS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 128); }
     fence_barrier_init();
@@ -146,14 +151,20 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   const Sched sch(blockIdx.x, gridDim.x, ntiles_total);
 
   // register budget per warpgroup (launch: 65536 / 384 = 168 each): the epilogue keeps a 128-value row of
-  // partial sums in registers (232), the producers hold PF + 1 chunks (168), loader and MMA warps need few (56)
+  // partial sums in registers (232), producers, loader and MMA warps need few
   if (warp < NPW) {
-    // =========================== A producer: global -> registers (PF chunks ahead) -> split -> smem ======
-    // thread -> rows warp*(8 RG) + g*8 + r8 (g < RG), k-groups hp*4 + kq (hp = 0, 1): 2 RG x 16 bytes per chunk
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // =========================== A producer =========================================================
+    // cp.async (16 bytes = one core-matrix row) global -> raw ring, DEPTH half-chunks ahead across work-item
+    // boundaries.  The fp32 tile itself is the tf32 high operand (the tensor core ignores the low 13
+    // mantissa bits); each thread then reads back ITS OWN pieces and writes lo = a - trunc_tf32(a).
+    // (Register prefetching was stuck at ~7 B/clk/SM no matter how many loads were nominally in flight,
+    // profiles/r01_gemm_roles.txt.)
+    // thread -> rows warp*32 + g*8 + r8 (g < 4), k-group kq: 4 x 16 bytes per half-chunk
     const int r8 = lane & 7, kq = lane >> 3;
     PROF_DECL
-    // prefetch cursor over the CTA's flat sequence of (N-tile q, M-tile mt, chunk c)
-    int pq = sch.q, pc = 0, pkch = 1, pK = 0;
+    // cursor over the CTA's flat sequence of (N-tile q, M-tile mt, half-chunk h)
+    int pq = sch.q, ph_ = 0, pnh = 1, pK = 0;
     int64_t pmt = sch.m_start, plda = 0;
     const float* pA = nullptr;
     bool pvalid = pq < sch.nq_total && sch.m_start < mtiles;
@@ -162,23 +173,25 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
       decode_q(descs, ndesc, pq, w);
       pA = a_base + w.d->a_off;
       plda = w.d->lda;
-      pkch = w.kchunks;
+      pnh = w.nh;
       pK = w.K;
     };
     if (pvalid) open_q();
-    auto fetch = [&](float4* dst) {  // load the cursor's chunk (if any) and advance
+    uint32_t n_issued = 0;
+    const int my_off = (warp * 4) * (KH / 4 * 32) + kq * 32 + r8 * 4;  // float offset of piece g = 0
+    auto issue = [&]() {  // cp.async the cursor's half-chunk (if any) into its raw stage, advance, commit
       if (pvalid) {
+        float* dst = S.araw[n_issued % RAW] + my_off;
+        const int k = ph_ * KH + kq * 4;
 #pragma unroll
         for (int g = 0; g < RG; ++g) {
-          const int64_t m = pmt * TM + warp * (8 * RG) + g * 8 + r8;
-#pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {
-            const int k = pc * KC + (hp * 4 + kq) * 4;
-            dst[g * 2 + hp] = (m < M && k < pK) ? ldg_stream(pA + m * plda + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const int64_t m = pmt * TM + warp * 32 + g * 8 + r8;
+          const bool in = m < M && k < pK;
+          cp_async16(dst + g * (KH / 4 * 32), in ? pA + m * plda + k : pA, in ? 16u : 0u);
         }
-        if (++pc == pkch) {
-          pc = 0;
+        ++n_issued;
+        if (++ph_ == pnh) {
+          ph_ = 0;
           pmt += sch.m_step;
           if (pmt >= mtiles) {
             pmt = sch.m_start;
@@ -188,41 +201,27 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
           }
         }
       }
+      cp_async_commit();
     };
-    float4 v[PF + 1][2 * RG];
-    bool ok[PF + 1];
+#pragma unroll 1
+    for (int j = 0; j < DEPTH; ++j) issue();
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_issued; ++i) {
+      PROF_WAIT(1, cp_async_wait<DEPTH - 1>())  // my pieces of half-chunk i have landed
+      // lo stage i % NLO was read by the MMAs of half-chunk i - 2 (this also frees raw stage (i + DEPTH) % RAW)
+      if (i >= NLO) PROF_WAIT(0, mbar_wait(&S.a_done[(i - NLO) % RAW], ((i - NLO) / RAW) & 1))
+      const float* raw = S.araw[i % RAW] + my_off;
+      float* lo = S.alo[i % NLO] + my_off;
 #pragma unroll
-    for (int p = 0; p < PF; ++p) { ok[p] = pvalid; fetch(v[p]); }
-    uint32_t it = 0;
-    bool done = false;
-    while (!done) {
-#pragma unroll
-      for (int p = 0; p <= PF; ++p) {
-        if (done) break;
-        ok[(p + PF) % (PF + 1)] = pvalid;
-        PROF_WAIT(1, fetch(v[(p + PF) % (PF + 1)]))
-        if (!ok[p]) { done = true; break; }
-        const uint32_t s = it % ASTAGES, ph = (it / ASTAGES) & 1;
-        if (it >= ASTAGES) PROF_WAIT(0, mbar_wait(&S.a_empty[s], ph ^ 1))
-        float* ahi = S.a[s];
-        float* alo = S.a[s] + TM * KC;
-#pragma unroll
-        for (int g = 0; g < RG; ++g) {
-#pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {
-            const int r = warp * (8 * RG) + g * 8 + r8, kg = hp * 4 + kq;
-            const float4 a = v[p][g * 2 + hp];
-            const float4 hi = make_float4(tf32_rn(a.x), tf32_rn(a.y), tf32_rn(a.z), tf32_rn(a.w));
-            const float4 lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
-            const int off = (r >> 3) * (KC / 4 * 32) + kg * 32 + (r & 7) * 4;
-            *reinterpret_cast<float4*>(ahi + off) = hi;
-            *reinterpret_cast<float4*>(alo + off) = lo;
-          }
-        }
-        PROF_WAIT(2, fence_proxy_async(); mbar_arrive(&S.a_full[s]))
-        ++it;
+      for (int g = 0; g < RG; ++g) {
+        const float4 a = *reinterpret_cast<const float4*>(raw + g * (KH / 4 * 32));
+        *reinterpret_cast<float4*>(lo + g * (KH / 4 * 32)) =
+            make_float4(tf32_lo(a.x), tf32_lo(a.y), tf32_lo(a.z), tf32_lo(a.w));
       }
+      PROF_WAIT(2, fence_proxy_async(); mbar_arrive(&S.a_full[i % RAW]))
+      issue();
     }
+    cp_async_wait<0>();
     if (warp == 0) PROF_END(0)
   } else if (warp < NPW + 4) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -236,7 +235,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
       WorkQ w;
       decode_q(descs, ndesc, q, w);
       const GemmDesc* d = w.d;
-      const int nseg = (w.kchunks + SEG_CHUNKS - 1) / SEG_CHUNKS;
+      const int nseg = (w.nh + SEG_H - 1) / SEG_H;
       const int ncols = w.ncols;
       const int64_t ldc = d->ldc;
       float* C = c_base + d->c_off + (int64_t)w.nt * TN;
@@ -372,11 +371,13 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
     // loops, which lets the compiler keep descriptors in uniform registers instead of broadcasting them
     // from lane 0 around each MMA; one elected lane issues; descriptors are built once and advanced by adds.
     const bool leader = elect_one();
-    constexpr uint32_t SBO = (KC / 4) * 128, LBO = 128;
-    const uint64_t dA0 = make_desc(smem_u32(S.a[0]), LBO, SBO);
-    const uint64_t dB0 = make_desc(smem_u32(S.b[0]), LBO, SBO);
-    constexpr uint64_t A_STAGE = (2 * TM * KC * sizeof(float)) >> 4, A_LO = (TM * KC * sizeof(float)) >> 4;
-    constexpr uint64_t B_SLOT = (BLOCK_FLOATS * sizeof(float)) >> 4, B_LO = (TN * KC * sizeof(float)) >> 4;
+    constexpr uint32_t SBO_A = (KH / 4) * 128, SBO_B = (KC / 4) * 128, LBO = 128;
+    const uint64_t dR0 = make_desc(smem_u32(S.araw[0]), LBO, SBO_A);
+    const uint64_t dL0 = make_desc(smem_u32(S.alo[0]), LBO, SBO_A);
+    const uint64_t dB0 = make_desc(smem_u32(S.b[0]), LBO, SBO_B);
+    constexpr uint32_t A_STAGE = (TM * KH * sizeof(float)) >> 4;
+    constexpr uint32_t B_SLOT = (BLOCK_FLOATS * sizeof(float)) >> 4, B_LO = (TN * KC * sizeof(float)) >> 4;
+    constexpr uint32_t B_HALF = (KH / 4 * 128) >> 4;  // the second 16 k of a weight chunk
     uint32_t it = 0, gseg = 0, bit = 0;
     uint32_t bpar = 0;  // per-slot bit: parity of the loads consumed (waited for)
     PROF_DECL
@@ -387,42 +388,41 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
       const uint32_t idesc = make_idesc(TM, nmma);
       bool first_mt = true;
       for (int64_t mt = sch.m_start; mt < mtiles; mt += sch.m_step) {
-        for (int c0 = 0; c0 < w.kchunks; c0 += SEG_CHUNKS, ++gseg) {
+        uint32_t slot = 0;
+        for (int h0 = 0; h0 < w.nh; h0 += SEG_H, ++gseg) {
           const uint32_t buf = gseg & 1;
           if (gseg >= 2) PROF_WAIT(0, mbar_wait(&S.acc_empty[buf], ((gseg >> 1) - 1) & 1))
           tc_fence_after();
           const uint32_t d_hh = tmem + buf * 256, d_x = d_hh + 128;
-          uint32_t fresh = 1;  // first chunk of the segment overwrites the accumulators
-          const int c1 = min(w.kchunks, c0 + SEG_CHUNKS);
-          for (int c = c0; c < c1; ++c, ++it) {
-            const uint32_t s = it % ASTAGES, ph = (it / ASTAGES) & 1;
-            uint32_t slot;
-            if (w.resident) {
-              slot = c;
-              if (first_mt) { PROF_WAIT(1, mbar_wait(&S.b_full[slot], (bpar >> slot) & 1)) bpar ^= 1u << slot; }
-            } else {
-              slot = bit % BSLOTS;
-              ++bit;
-              PROF_WAIT(1, mbar_wait(&S.b_full[slot], (bpar >> slot) & 1))
-              bpar ^= 1u << slot;
+          uint32_t fresh = 1;  // the first half-chunk of a segment overwrites the accumulators
+          const int h1 = min(w.nh, h0 + SEG_H);
+          for (int h = h0; h < h1; ++h, ++it) {
+            const uint32_t s = it % RAW, ph = (it / RAW) & 1, half = h & 1;
+            if (!half) {  // first half of a weight chunk
+              if (w.resident) {
+                slot = h >> 1;
+                if (first_mt) { PROF_WAIT(1, mbar_wait(&S.b_full[slot], (bpar >> slot) & 1)) bpar ^= 1u << slot; }
+              } else {
+                slot = bit % BSLOTS;
+                ++bit;
+                PROF_WAIT(1, mbar_wait(&S.b_full[slot], (bpar >> slot) & 1))
+                bpar ^= 1u << slot;
+              }
             }
             PROF_WAIT(2, mbar_wait(&S.a_full[s], ph))
             tc_fence_after();
-            const uint64_t a_hi = dA0 + (uint64_t)(s * (uint32_t)A_STAGE), a_lo = a_hi + A_LO;
-            const uint64_t b_hi = dB0 + (uint64_t)(slot * (uint32_t)B_SLOT), b_lo = b_hi + B_LO;
+            const uint64_t a_hi = dR0 + (uint64_t)(s * A_STAGE), a_lo = dL0 + (uint64_t)((it % NLO) * A_STAGE);
+            const uint64_t b_hi = dB0 + (uint64_t)(slot * B_SLOT + half * B_HALF), b_lo = b_hi + B_LO;
             if (leader) {
-              // k-step advance = 256 bytes = 16 descriptor units
+              // k-step advance = 2 core matrices = 256 bytes = 16 descriptor units
               umma_tf32(d_hh, a_hi, b_hi, idesc, fresh ^ 1);
               umma_tf32(d_x, a_lo, b_hi, idesc, fresh ^ 1);
               umma_tf32_acc(d_x, a_hi, b_lo, idesc);
-#pragma unroll
-              for (int ks = 1; ks < KC / 8; ++ks) {
-                umma_tf32_acc(d_hh, a_hi + ks * 16, b_hi + ks * 16, idesc);
-                umma_tf32_acc(d_x, a_lo + ks * 16, b_hi + ks * 16, idesc);
-                umma_tf32_acc(d_x, a_hi + ks * 16, b_lo + ks * 16, idesc);
-              }
-              umma_commit(&S.a_empty[s]);
-              if (!w.resident) umma_commit(&S.b_empty[slot]);
+              umma_tf32_acc(d_hh, a_hi + 16, b_hi + 16, idesc);
+              umma_tf32_acc(d_x, a_lo + 16, b_hi + 16, idesc);
+              umma_tf32_acc(d_x, a_hi + 16, b_lo + 16, idesc);
+              umma_commit(&S.a_done[s]);
+              if (!w.resident && (half || h == w.nh - 1)) umma_commit(&S.b_empty[slot]);
             }
             fresh = 0;
             __syncwarp();

@@ -374,44 +374,53 @@ k_mlp_bwd(const float* __restrict__ emb, const float* __restrict__ W1s, const fl
 //   gemb[e, k] = sum_m gh[e, m] * silu'(pre[e, m]) * W1s[k, m],  pre recomputed from emb
 // (feeds / follows the grouped tensor-core GEMM of the second layer, nqb_gemm.cu)
 // ---------------------------------------------------------------------------------------------
+// Persistent warps: lane = 4 hidden units whose 8 x 4 first-layer weights live in registers for the whole
+// kernel; a warp walks over edges (grid-stride), reads the 8 basis values of the edge (one broadcast
+// 32-byte load) and writes the edge's 128 activations as one 512-byte row.  (The first version re-staged
+// the 4 KB weight matrix per 8 edges -- as many bytes as it wrote.)
+__device__ __forceinline__ float sigmoid_fast(float p) { return __fdividef(1.0f, 1.0f + expf(-p)); }
+
 __global__ void __launch_bounds__(256) k_hidden_fwd(const float* __restrict__ emb, const float* __restrict__ W1s,
                                                     int64_t E, float* __restrict__ h) {
-  __shared__ float w1[NB * H];
-  for (int i = threadIdx.x; i < NB * H; i += blockDim.x) w1[i] = W1s[i];
-  __syncthreads();
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 4 hidden units of one edge
-  const int64_t e = gid >> 5;
-  const int m0 = (int)(gid & 31) * 4;
-  if (e >= E) return;
-  float x[NB];
-  const float4 x0 = __ldg(reinterpret_cast<const float4*>(emb + e * NB));
-  const float4 x1 = __ldg(reinterpret_cast<const float4*>(emb + e * NB + 4));
-  x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
-  float o[4];
+  const int lane = threadIdx.x & 31, m0 = lane * 4;
+  float w[NB][4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float p = 0.f;
-#pragma unroll
-    for (int k = 0; k < NB; ++k) p = fmaf(x[k], w1[k * H + m0 + q], p);
-    o[q] = silu_f(p);
+  for (int k = 0; k < NB; ++k) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(W1s + k * H + m0));
+    w[k][0] = t.x; w[k][1] = t.y; w[k][2] = t.z; w[k][3] = t.w;
   }
-  *reinterpret_cast<float4*>(h + e * H + m0) = make_float4(o[0], o[1], o[2], o[3]);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < E; e += nwarps) {
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(emb + e * NB));
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(emb + e * NB + 4));
+    const float x[NB] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float p = 0.f;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) p = fmaf(x[k], w[k][q], p);
+      o[q] = p * sigmoid_fast(p);
+    }
+    __stcs(reinterpret_cast<float4*>(h + e * H + m0), make_float4(o[0], o[1], o[2], o[3]));
+  }
 }
 
 __global__ void __launch_bounds__(256) k_hidden_bwd(const float* __restrict__ emb, const float* __restrict__ W1s,
                                                     const float* __restrict__ gh, int64_t E, float* __restrict__ gemb) {
-  __shared__ float w1[NB * H];
-  for (int i = threadIdx.x; i < NB * H; i += blockDim.x) w1[i] = W1s[i];
-  __syncthreads();
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // warp = one edge, lane = 4 hidden units
-  const int64_t e = gid >> 5;
   const int lane = threadIdx.x & 31, m0 = lane * 4;
-  if (e >= E) return;  // whole warp exits together (E is tested per warp)
-  float x[NB];
+  float w[NB][4];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(W1s + k * H + m0));
+    w[k][0] = t.x; w[k][1] = t.y; w[k][2] = t.z; w[k][3] = t.w;
+  }
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < E; e += nwarps) {  // warp = edge
   const float4 x0 = __ldg(reinterpret_cast<const float4*>(emb + e * NB));
   const float4 x1 = __ldg(reinterpret_cast<const float4*>(emb + e * NB + 4));
-  x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
-  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gh + e * H + m0));
+  const float x[NB] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  const float4 g4 = __ldcs(reinterpret_cast<const float4*>(gh + e * H + m0));
   const float g[4] = {g4.x, g4.y, g4.z, g4.w};
   float acc[NB];
 #pragma unroll
@@ -420,11 +429,11 @@ __global__ void __launch_bounds__(256) k_hidden_bwd(const float* __restrict__ em
   for (int q = 0; q < 4; ++q) {
     float p = 0.f;
 #pragma unroll
-    for (int k = 0; k < NB; ++k) p = fmaf(x[k], w1[k * H + m0 + q], p);
-    const float sg = 1.0f / (1.0f + expf(-p));
+    for (int k = 0; k < NB; ++k) p = fmaf(x[k], w[k][q], p);
+    const float sg = sigmoid_fast(p);
     const float gp = g[q] * (sg * (1.0f + p * (1.0f - sg)));
 #pragma unroll
-    for (int k = 0; k < NB; ++k) acc[k] = fmaf(gp, w1[k * H + m0 + q], acc[k]);
+    for (int k = 0; k < NB; ++k) acc[k] = fmaf(gp, w[k][q], acc[k]);
   }
   // reduce the 8 partial sums over the 32 lanes (halving butterfly: 4 + 2 + 1 + 2 shuffles)
 #pragma unroll
@@ -449,6 +458,7 @@ __global__ void __launch_bounds__(256) k_hidden_bwd(const float* __restrict__ em
     const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     gemb[e * NB + k] = acc[0];
   }
+  }  // edge loop
 }
 
 }  // namespace
@@ -531,6 +541,19 @@ extern "C" int nqb_mlp_bwd(const float* emb, const float* W1s, const float* prep
   return 0;
 }
 
+// persistent grid: 8 CTAs of 256 threads per SM (or fewer when there is less work)
+static unsigned hidden_grid(int64_t threads) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int64_t need = (threads + 255) / 256, cap = (int64_t)sms * 8;
+  return (unsigned)(need < cap ? need : cap);
+}
+
 extern "C" int nqb_mlp_hidden_fwd(const float* emb, const float* W1s, int64_t E, int num_bessel, int hidden, float* h,
                                   nqb_stream_t st) {
   if (num_bessel != NB || hidden != H) return nqb_set_error("nqb_mlp_hidden_fwd: only num_bessel=8, hidden=128 is built");
@@ -538,7 +561,7 @@ extern "C" int nqb_mlp_hidden_fwd(const float* emb, const float* W1s, int64_t E,
   if (E == 0) return 0;
   if (!emb || !W1s || !h) return nqb_set_error("nqb_mlp_hidden_fwd: null pointer");
   const int64_t threads = E * 32;
-  k_hidden_fwd<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)st>>>(emb, W1s, E, h);
+  k_hidden_fwd<<<hidden_grid(threads), 256, 0, (cudaStream_t)st>>>(emb, W1s, E, h);
   nqb_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
@@ -552,7 +575,7 @@ extern "C" int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const floa
   if (E == 0) return 0;
   if (!emb || !W1s || !grad_h || !grad_emb) return nqb_set_error("nqb_mlp_hidden_bwd: null pointer");
   const int64_t threads = E * 32;
-  k_hidden_bwd<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)st>>>(emb, W1s, grad_h, E, grad_emb);
+  k_hidden_bwd<<<hidden_grid(threads), 256, 0, (cudaStream_t)st>>>(emb, W1s, grad_h, E, grad_emb);
   nqb_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
