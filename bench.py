@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--decomp", default="frames", choices=["frames", "halo"],
                     help="N>1: 'frames' = one independent frame per GPU (the reference's DDP axis); 'halo' = ONE frame "
                          "of N x atoms_per_gpu atoms, slab-partitioned, per-layer NCCL halo exchange + energy/force all-reduce")
+    ap.add_argument("--no-graph", action="store_true", help="eager step (no CUDA-graph replay)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one warm-up step, then ONE step between cudaProfilerStart/Stop (for ncu "
                          "--profile-from-start off); prints no bench line")
@@ -260,7 +261,19 @@ def main():
     if halo_mode:
         halo = P.HaloExchange(plan, dev)
 
+    graphed = None
+    if not halo_mode and not args.no_graph:
+        from nequip_b200.graph import GraphedEnergyForces
+
+        graphed = GraphedEnergyForces(model, resident)  # captured once; replayed every step
+
     def step_resident():
+        if graphed is not None:
+            out = graphed.replay()
+            if world > 1:
+                e_buf.copy_(out["total_energy"].view(-1))
+                dist.all_reduce(e_buf)
+            return out
         if halo_mode:
             e, f = P.sharded_energy_forces(model, resident, plan, halo)
             return {"total_energy": e, "forces": f}
@@ -274,6 +287,14 @@ def main():
     e_host = torch.empty((1,), dtype=torch.float64).pin_memory()
 
     def step_e2e():
+        if graphed is not None:
+            out = graphed(host)  # pinned host -> static device buffers (H2D) -> replay
+            if world > 1:
+                e_buf.copy_(out["total_energy"].view(-1))
+                dist.all_reduce(e_buf)
+            f_host.copy_(out["forces"], non_blocking=True)
+            e_host.copy_(out["total_energy"].view(-1), non_blocking=True)
+            return out
         d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
         if halo_mode:
             e, f = P.sharded_energy_forces(model, d, plan, halo, reduce_forces=False)
@@ -305,6 +326,8 @@ def main():
             dist.barrier()
         ms = e0.elapsed_time(e1) / steps
         launches = _capi.launch_count() - n0
+        if graphed is not None:
+            launches += graphed.launches_per_replay * steps  # kernels inside the replayed graph
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -326,6 +349,8 @@ def main():
     ms_res, launches = timed(step_resident, args.steps, args.warmup)
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
+    if graphed is not None:
+        graphed.check_sorted()  # the in-graph "edges grouped by destination" flag of the last replay
 
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     d2h = f_host.numel() * 8 + 8
@@ -408,6 +433,8 @@ def main():
                 "parallelism": (f"halo{world}: one {total_atoms}-atom frame in {world} x-slabs, {plan.n_own} owned + "
                                 f"{plan.n_ghost} ghost atoms on rank 0, per-layer NCCL halo exchange" if halo_mode
                                 else f"dp{world} over frames (one {n_atoms}-atom frame per GPU)"),
+                "launch": ("one CUDA-graph replay per step (nequip_b200/graph.py)" if graphed is not None
+                           else "eager launches"),
                 "l2_policy": "inputs larger than L2 (edge weights of one layer: %.2f GB)" % (
                     n_edges * max(l.conv.tp_scatter.weight_numel for l in model.layers) * 4 / 1e9),
             },

@@ -15,7 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import threading
 from dataclasses import dataclass
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -126,6 +126,14 @@ def build_csr(edge_dst: torch.Tensor, num_nodes: int, assume_sorted: Optional[bo
     L = _capi.lib()
     st = _stream()
     is_sorted = assume_sorted
+    deferred = getattr(_sorted_tls, "flags", None)
+    if is_sorted is None and deferred is not None:
+        # CUDA-graph capture (nequip_b200/graph.py): no host sync allowed -- run the check kernel, keep its
+        # flag for the caller to verify after the replay, and build the CSR as if sorted
+        flag = torch.empty(1, dtype=torch.int32, device=edge_dst.device)
+        _capi.check(L.nqb_csr_check_sorted(_ptr(edge_dst), E, _ptr(flag), st), "nqb_csr_check_sorted")
+        deferred.append(flag)
+        is_sorted = True
     if is_sorted is None:
         flag = torch.empty(1, dtype=torch.int32, device=edge_dst.device)
         _capi.check(L.nqb_csr_check_sorted(_ptr(edge_dst), E, _ptr(flag), st), "nqb_csr_check_sorted")
@@ -139,6 +147,24 @@ def build_csr(edge_dst: torch.Tensor, num_nodes: int, assume_sorted: Optional[bo
     row_ptr = torch.empty(num_nodes + 1, dtype=torch.int64, device=edge_dst.device)
     _capi.check(L.nqb_csr_from_sorted(_ptr(keys), E, num_nodes, _ptr(row_ptr), st), "nqb_csr_from_sorted")
     return EdgeCSR(row_ptr, perm, num_nodes, E)
+
+
+_sorted_tls = threading.local()
+
+
+class deferred_sorted_check:
+    """Context manager: inside it ``build_csr`` does not synchronise to learn whether the edge list is grouped
+    by destination; it records the device flags (1 = sorted) in ``self.flags`` and assumes sorted."""
+
+    def __enter__(self):
+        self.flags: List[torch.Tensor] = []
+        self._prev = getattr(_sorted_tls, "flags", None)
+        _sorted_tls.flags = self.flags
+        return self
+
+    def __exit__(self, *exc):
+        _sorted_tls.flags = self._prev
+        return False
 
 
 class _CSRCache:
