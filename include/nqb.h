@@ -139,8 +139,10 @@ int nqb_mlp_bwd(const float* emb, const float* W1s, const float* prep_bwd, const
 /* First radial layer (K = 8, CUDA cores):  h[E,128] = silu(emb[E,8] @ W1s[8,128])  and
  * grad_emb[E,8] = (grad_h * silu'(emb @ W1s)) @ W1s^T  (pre-activation recomputed, nothing saved).
  * Together with nqb_gemm_grouped for the second layer this is ScalarMLPFunction (nequip/nn/mlp.py:80-195). */
+/* h_lo (nullable): the part of h the tensor core does not see, h_lo = rna_tf32(h - trunc_tf32(h)); handing it
+ * to nqb_gemm_grouped as a_lo_base saves that kernel the operand-split pass. */
 int nqb_mlp_hidden_fwd(const float* emb, const float* W1s, int64_t E, int num_bessel, int hidden, float* h,
-                       nqb_stream_t st);
+                       float* h_lo, nqb_stream_t st);
 int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const float* grad_h, int64_t E, int num_bessel,
                        int hidden, float* grad_emb, nqb_stream_t st);
 
@@ -153,13 +155,15 @@ int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const float* grad_h, 
  *   {a_off, c_off, b_off, rs_off (row of the [R, rs_ld] row-scale matrix, -1 = none), lda, ldc, K, N, kchunks=ceil(K/32), ntiles=ceil(N/128),
  *    tile0 (prefix sum of ntiles), flags (bit0: accumulate into C)};  offsets in floats from the bases.
  * Requirements: K, N, lda, ldc, a_off, c_off multiples of 4; bases 16-byte aligned.
- * B_p is prepared once (split hi/lo, tiled) with nqb_gemm_prepare into nqb_gemm_prepared_floats(K,N) floats. */
+ * B_p is prepared once (split hi/lo, tiled) with nqb_gemm_prepare into nqb_gemm_prepared_floats(K,N) floats.
+ * a_lo_base (nullable): pre-split low parts of A, same offsets/strides as a_base (see nqb_mlp_hidden_fwd);
+ * when null the kernel derives them itself. */
 int64_t nqb_gemm_prepared_floats(int K, int N);
 int nqb_gemm_prepare(const float* B, int64_t ldb, int K, int N, int transposed, float scale, float* prepared,
                      nqb_stream_t st);
 int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const float* a_base,
-                     const float* prepared_base, float* c_base, const float* rowscale_base, int64_t rs_ld,
-                     int64_t M, nqb_stream_t st);
+                     const float* a_lo_base, const float* prepared_base, float* c_base,
+                     const float* rowscale_base, int64_t rs_ld, int64_t M, nqb_stream_t st);
 
 /* number of kernels the library has launched in this process (bench accounting) */
 int64_t nqb_launch_count(void);

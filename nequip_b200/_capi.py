@@ -7,6 +7,7 @@ error propagates.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 from . import build
@@ -48,11 +49,11 @@ SIGNATURES = {
         _i32, [_i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     "nqb_edge_embed_bwd": (
         _i32, [_i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "nqb_mlp_hidden_fwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "nqb_mlp_hidden_fwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "nqb_mlp_hidden_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "nqb_gemm_prepared_floats": (_i64, [_i32, _i32]),
     "nqb_gemm_prepare": (_i32, [_vp, _i64, _i32, _i32, _i32, C.c_float, _vp, _vp]),
-    "nqb_gemm_grouped": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "nqb_gemm_grouped": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "nqb_mlp_prepared_bytes": (C.c_size_t, [_i32]),
     "nqb_mlp_prepare": (_i32, [_vp, C.c_float, _i32, _i32, _vp, _vp, _vp]),
     "nqb_mlp_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
@@ -64,7 +65,8 @@ def lib() -> C.CDLL:
     """Load (building first if needed) libnqb.so."""
     global _lib
     if _lib is None:
-        path = build.ensure_runtime()
+        # NQB_RUNTIME_LIB: load an alternative build of the same sources (kernel-variant experiments)
+        path = os.environ.get("NQB_RUNTIME_LIB") or build.ensure_runtime()
         L = C.CDLL(path, mode=C.RTLD_GLOBAL)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the symbol is missing

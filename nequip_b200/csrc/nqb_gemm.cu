@@ -54,17 +54,26 @@ __device__ unsigned long long g_prof[16];
 constexpr int TM = 128;          // rows per tile
 constexpr int TN = 128;          // max columns per tile
 constexpr int KC = 32;           // K chunk
-constexpr int KH = 16;           // A is staged in half-chunks of 16 k
-constexpr int RAW = 6;           // ring of raw A half-chunks (8 KB each), filled by cp.async
-constexpr int DEPTH = 4;         // half-chunks in flight per CTA (32 KB)
-constexpr int NLO = 2;           // ring of A low-part half-chunks
+#ifndef NQB_KH
+#define NQB_KH 16
+#define NQB_RAW 5
+#define NQB_NLO 5
+#define NQB_DEPTH 3
+#endif
+constexpr int KH = NQB_KH;       // A is staged in pieces of KH k (16 or 32 = half or whole weight chunk)
+constexpr int RAW = NQB_RAW;     // ring of raw A pieces (TM x KH fp32), filled by cp.async
+constexpr int DEPTH = NQB_DEPTH; // pieces in flight per CTA
+constexpr int NLO = NQB_NLO;     // ring of A low-part pieces
+constexpr int HPC = 32 / KH;     // pieces per weight chunk
+static_assert(KH == 16 || KH == 32, "KH");
+static_assert(DEPTH <= RAW - 1, "ring depth");
+constexpr bool PRESPLIT_OK = NLO >= RAW;  // pre-split mode refills both rings at the same distance
 constexpr int BSLOTS = 4;        // B slots: a ring when K > 128, resident per N-tile when K <= 128
-constexpr int SEG_H = 20;        // half-chunks per accumulation segment (40 accumulate steps on the hi*hi accumulator)
+constexpr int SEG_H = 320 / KH;  // pieces per accumulation segment (40 accumulate steps on the hi*hi accumulator)
 constexpr int NPW = 4;            // producer warps
 constexpr int NPROD = NPW * 32;   // producer threads
 constexpr int NTHREADS = NPROD + 256;  // + epilogue warpgroup + {loader, MMA, 2 idle} warps
 constexpr int RG = TM / NPW / 8;  // 8-row groups per producer warp
-static_assert(DEPTH <= RAW - 2, "a raw stage is refilled two half-chunks after its MMA was issued");
 constexpr int BLOCK_FLOATS = 2 * TN * KC;  // one prepared weight block: [hi | lo] x [128 x 32]
 
 struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
@@ -75,8 +84,8 @@ struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
 };
 
 struct Smem {
-  float araw[RAW][TM * KH];        // 6 x 8 KB: fp32 A half-chunks, canonical K-major core-matrix layout
-  float alo[NLO][TM * KH];         // 2 x 8 KB: their tf32 low parts
+  float araw[RAW][TM * KH];        // 5 x 8 KB: fp32 A pieces, canonical K-major core-matrix layout
+  float alo[NLO][TM * KH];         // 5 x 8 KB: their tf32 low parts
   float b[BSLOTS][BLOCK_FLOATS];   // 4 x 32 KB
   float stage[4][32 * 32];         // epilogue staging, one 32x32 tile per warp (swizzled)
   uint64_t a_full[RAW], a_done[RAW];
@@ -130,7 +139,7 @@ __device__ __forceinline__ void decode_q(const GemmDesc* descs, int ndesc, int q
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const float* __restrict__ a_base,
-         const float* __restrict__ b_base, float* __restrict__ c_base, const float* __restrict__ rs_base, int64_t rs_ld,
+         const float* __restrict__ a_lo_base, const float* __restrict__ b_base, float* __restrict__ c_base, const float* __restrict__ rs_base, int64_t rs_ld,
          int64_t M) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -167,27 +176,39 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
     int pq = sch.q, ph_ = 0, pnh = 1, pK = 0;
     int64_t pmt = sch.m_start, plda = 0;
     const float* pA = nullptr;
+    const float* pAlo = nullptr;
+    const bool presplit = PRESPLIT_OK && a_lo_base != nullptr;  // caller-supplied low parts: producers only copy
     bool pvalid = pq < sch.nq_total && sch.m_start < mtiles;
     auto open_q = [&]() {
       WorkQ w;
       decode_q(descs, ndesc, pq, w);
       pA = a_base + w.d->a_off;
+      if (presplit) pAlo = a_lo_base + w.d->a_off;
       plda = w.d->lda;
       pnh = w.nh;
       pK = w.K;
     };
     if (pvalid) open_q();
     uint32_t n_issued = 0;
-    const int my_off = (warp * 4) * (KH / 4 * 32) + kq * 32 + r8 * 4;  // float offset of piece g = 0
-    auto issue = [&]() {  // cp.async the cursor's half-chunk (if any) into its raw stage, advance, commit
+    const int my_off = (warp * 4) * (KH / 4 * 32) + kq * 32 + r8 * 4;  // float offset of piece (g = 0, kh = 0)
+    constexpr int KQ = KH / 16;  // 16-k halves per piece: k-group = kh * 4 + kq
+    auto issue = [&]() {  // cp.async the cursor's piece (if any) into its raw stage, advance, commit
       if (pvalid) {
         float* dst = S.araw[n_issued % RAW] + my_off;
-        const int k = ph_ * KH + kq * 4;
+        float* dlo = S.alo[n_issued % NLO] + my_off;
 #pragma unroll
         for (int g = 0; g < RG; ++g) {
           const int64_t m = pmt * TM + warp * 32 + g * 8 + r8;
-          const bool in = m < M && k < pK;
-          cp_async16(dst + g * (KH / 4 * 32), in ? pA + m * plda + k : pA, in ? 16u : 0u);
+#pragma unroll
+          for (int kh = 0; kh < KQ; ++kh) {
+            const int k = ph_ * KH + (kh * 4 + kq) * 4;
+            const bool in = m < M && k < pK;
+            const int64_t off = in ? m * plda + k : 0;
+#ifndef NQB_X_NOLOAD
+            cp_async16(dst + g * (KH / 4 * 32) + kh * 128, pA + off, in ? 16u : 0u);
+#endif
+            if (presplit) cp_async16(dlo + g * (KH / 4 * 32) + kh * 128, pAlo + off, in ? 16u : 0u);
+          }
         }
         ++n_issued;
         if (++ph_ == pnh) {
@@ -208,17 +229,31 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
 #pragma unroll 1
     for (uint32_t i = 0; i < n_issued; ++i) {
       PROF_WAIT(1, cp_async_wait<DEPTH - 1>())  // my pieces of half-chunk i have landed
-      // lo stage i % NLO was read by the MMAs of half-chunk i - 2 (this also frees raw stage (i + DEPTH) % RAW)
-      if (i >= NLO) PROF_WAIT(0, mbar_wait(&S.a_done[(i - NLO) % RAW], ((i - NLO) / RAW) & 1))
-      const float* raw = S.araw[i % RAW] + my_off;
-      float* lo = S.alo[i % NLO] + my_off;
+#ifndef NQB_X_NOLO
+      if (!presplit) {
+        // lo stage i % NLO was read by the MMAs of piece i - NLO
+        if (i >= NLO) PROF_WAIT(0, mbar_wait(&S.a_done[(i - NLO) % RAW], ((i - NLO) / RAW) & 1))
+        const float* raw = S.araw[i % RAW] + my_off;
+        float* lo = S.alo[i % NLO] + my_off;
+        float4 a[RG * KQ];
 #pragma unroll
-      for (int g = 0; g < RG; ++g) {
-        const float4 a = *reinterpret_cast<const float4*>(raw + g * (KH / 4 * 32));
-        *reinterpret_cast<float4*>(lo + g * (KH / 4 * 32)) =
-            make_float4(tf32_lo(a.x), tf32_lo(a.y), tf32_lo(a.z), tf32_lo(a.w));
+        for (int g = 0; g < RG; ++g)
+#pragma unroll
+          for (int kh = 0; kh < KQ; ++kh) a[g * KQ + kh] = *reinterpret_cast<const float4*>(raw + g * (KH / 4 * 32) + kh * 128);
+#pragma unroll
+        for (int g = 0; g < RG; ++g)
+#pragma unroll
+          for (int kh = 0; kh < KQ; ++kh) {
+            const float4 t = a[g * KQ + kh];
+            *reinterpret_cast<float4*>(lo + g * (KH / 4 * 32) + kh * 128) =
+                make_float4(tf32_lo(t.x), tf32_lo(t.y), tf32_lo(t.z), tf32_lo(t.w));
+          }
       }
+#endif
       PROF_WAIT(2, fence_proxy_async(); mbar_arrive(&S.a_full[i % RAW]))
+      // raw stage (i + DEPTH) % RAW was last read by the MMAs of piece i + DEPTH - RAW
+      if (i + DEPTH >= RAW)
+        PROF_WAIT(0, mbar_wait(&S.a_done[(i + DEPTH - RAW) % RAW], ((i + DEPTH - RAW) / RAW) & 1))
       issue();
     }
     cp_async_wait<0>();
@@ -303,8 +338,12 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) hh[j] += xx[j];
+#ifndef NQB_X_NOEMIT
             if (reduce) PROF_WAIT(2, emit(std::integral_constant<int, 1>{}, cb, hh))
             else PROF_WAIT(2, emit(std::integral_constant<int, 0>{}, cb, hh))
+#else
+            if (hh[0] == 123.456f) emit(std::integral_constant<int, 0>{}, cb, hh);
+#endif
           }
           ++gseg;
         } else {
@@ -377,7 +416,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
     const uint64_t dB0 = make_desc(smem_u32(S.b[0]), LBO, SBO_B);
     constexpr uint32_t A_STAGE = (TM * KH * sizeof(float)) >> 4;
     constexpr uint32_t B_SLOT = (BLOCK_FLOATS * sizeof(float)) >> 4, B_LO = (TN * KC * sizeof(float)) >> 4;
-    constexpr uint32_t B_HALF = (KH / 4 * 128) >> 4;  // the second 16 k of a weight chunk
+    constexpr uint32_t B_HALF = (KH / 4 * 128) >> 4;  // the second piece of a weight chunk (KH = 16)
     uint32_t it = 0, gseg = 0, bit = 0;
     uint32_t bpar = 0;  // per-slot bit: parity of the loads consumed (waited for)
     PROF_DECL
@@ -397,10 +436,10 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
           uint32_t fresh = 1;  // the first half-chunk of a segment overwrites the accumulators
           const int h1 = min(w.nh, h0 + SEG_H);
           for (int h = h0; h < h1; ++h, ++it) {
-            const uint32_t s = it % RAW, ph = (it / RAW) & 1, half = h & 1;
-            if (!half) {  // first half of a weight chunk
+            const uint32_t s = it % RAW, ph = (it / RAW) & 1, half = h % HPC;
+            if (!half) {  // first piece of a weight chunk
               if (w.resident) {
-                slot = h >> 1;
+                slot = h / HPC;
                 if (first_mt) { PROF_WAIT(1, mbar_wait(&S.b_full[slot], (bpar >> slot) & 1)) bpar ^= 1u << slot; }
               } else {
                 slot = bit % BSLOTS;
@@ -414,15 +453,36 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
             const uint64_t a_hi = dR0 + (uint64_t)(s * A_STAGE), a_lo = dL0 + (uint64_t)((it % NLO) * A_STAGE);
             const uint64_t b_hi = dB0 + (uint64_t)(slot * B_SLOT + half * B_HALF), b_lo = b_hi + B_LO;
             if (leader) {
-              // k-step advance = 2 core matrices = 256 bytes = 16 descriptor units
+#ifndef NQB_X_NOMMA
+              // k-step advance = 2 core matrices = 256 bytes = 16 descriptor units.  MMAs on the same
+              // accumulator are issued back to back: switching accumulators costs tensor-pipe time
+#ifndef NQB_X_ORDER
+#define NQB_X_ORDER 1
+#endif
+#if NQB_X_ORDER == 0
               umma_tf32(d_hh, a_hi, b_hi, idesc, fresh ^ 1);
               umma_tf32(d_x, a_lo, b_hi, idesc, fresh ^ 1);
               umma_tf32_acc(d_x, a_hi, b_lo, idesc);
-              umma_tf32_acc(d_hh, a_hi + 16, b_hi + 16, idesc);
-              umma_tf32_acc(d_x, a_lo + 16, b_hi + 16, idesc);
-              umma_tf32_acc(d_x, a_hi + 16, b_lo + 16, idesc);
+#pragma unroll
+              for (int ks = 1; ks < KH / 8; ++ks) {
+                umma_tf32_acc(d_hh, a_hi + ks * 16, b_hi + ks * 16, idesc);
+                umma_tf32_acc(d_x, a_lo + ks * 16, b_hi + ks * 16, idesc);
+                umma_tf32_acc(d_x, a_hi + ks * 16, b_lo + ks * 16, idesc);
+              }
+#else
+              const uint32_t d_x2 = (NQB_X_ORDER == 2) ? d_hh : d_x;  // ORDER 2: timing experiment only
+              umma_tf32(d_hh, a_hi, b_hi, idesc, fresh ^ 1);
+#pragma unroll
+              for (int ks = 1; ks < KH / 8; ++ks) umma_tf32_acc(d_hh, a_hi + ks * 16, b_hi + ks * 16, idesc);
+              umma_tf32(d_x2, a_lo, b_hi, idesc, fresh ^ 1);
+#pragma unroll
+              for (int ks = 1; ks < KH / 8; ++ks) umma_tf32_acc(d_x2, a_lo + ks * 16, b_hi + ks * 16, idesc);
+#pragma unroll
+              for (int ks = 0; ks < KH / 8; ++ks) umma_tf32_acc(d_x2, a_hi + ks * 16, b_lo + ks * 16, idesc);
+#endif
+#endif
               umma_commit(&S.a_done[s]);
-              if (!w.resident && (half || h == w.nh - 1)) umma_commit(&S.b_empty[slot]);
+              if (!w.resident && (half == HPC - 1 || h == w.nh - 1)) umma_commit(&S.b_empty[slot]);
             }
             fresh = 0;
             __syncwarp();
@@ -507,8 +567,8 @@ extern "C" int nqb_gemm_prepare(const float* B, int64_t ldb, int K, int N, int t
 }
 
 extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const float* a_base,
-                                const float* prepared_base, float* c_base, const float* rowscale_base, int64_t rs_ld,
-                                int64_t M, nqb_stream_t st) {
+                                const float* a_lo_base, const float* prepared_base, float* c_base,
+                                const float* rowscale_base, int64_t rs_ld, int64_t M, nqb_stream_t st) {
   if (ndesc <= 0 || ntiles_total <= 0) return nqb_set_error("nqb_gemm_grouped: empty problem list");
   if (M < 0) return nqb_set_error("nqb_gemm_grouped: negative M");
   if (M == 0) return 0;
@@ -521,7 +581,7 @@ extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_tot
   }
   const int64_t nwork = ((M + TM - 1) / TM) * (int64_t)ntiles_total;
   const int grid = (int)(nwork < gemm_sm_count() ? nwork : gemm_sm_count());
-  k_gemm3x<<<grid, 384, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, a_base,
+  k_gemm3x<<<grid, 384, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, a_base, a_lo_base,
                                                                  prepared_base, c_base, rowscale_base, rs_ld, M);
   nqb_count_launch();
   cudaError_t e = cudaGetLastError();

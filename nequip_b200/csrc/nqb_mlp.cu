@@ -381,7 +381,7 @@ k_mlp_bwd(const float* __restrict__ emb, const float* __restrict__ W1s, const fl
 __device__ __forceinline__ float sigmoid_fast(float p) { return __fdividef(1.0f, 1.0f + expf(-p)); }
 
 __global__ void __launch_bounds__(256) k_hidden_fwd(const float* __restrict__ emb, const float* __restrict__ W1s,
-                                                    int64_t E, float* __restrict__ h) {
+                                                    int64_t E, float* __restrict__ h, float* __restrict__ h_lo) {
   const int lane = threadIdx.x & 31, m0 = lane * 4;
   float w[NB][4];
 #pragma unroll
@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(256) k_hidden_fwd(const float* __restrict__ em
       o[q] = p * sigmoid_fast(p);
     }
     __stcs(reinterpret_cast<float4*>(h + e * H + m0), make_float4(o[0], o[1], o[2], o[3]));
+    if (h_lo) __stcs(reinterpret_cast<float4*>(h_lo + e * H + m0), make_float4(tf32_lo(o[0]), tf32_lo(o[1]), tf32_lo(o[2]), tf32_lo(o[3])));
   }
 }
 
@@ -555,13 +556,13 @@ static unsigned hidden_grid(int64_t threads) {
 }
 
 extern "C" int nqb_mlp_hidden_fwd(const float* emb, const float* W1s, int64_t E, int num_bessel, int hidden, float* h,
-                                  nqb_stream_t st) {
+                                  float* h_lo, nqb_stream_t st) {
   if (num_bessel != NB || hidden != H) return nqb_set_error("nqb_mlp_hidden_fwd: only num_bessel=8, hidden=128 is built");
   if (E < 0) return nqb_set_error("nqb_mlp_hidden_fwd: negative size");
   if (E == 0) return 0;
   if (!emb || !W1s || !h) return nqb_set_error("nqb_mlp_hidden_fwd: null pointer");
   const int64_t threads = E * 32;
-  k_hidden_fwd<<<hidden_grid(threads), 256, 0, (cudaStream_t)st>>>(emb, W1s, E, h);
+  k_hidden_fwd<<<hidden_grid(threads), 256, 0, (cudaStream_t)st>>>(emb, W1s, E, h, h_lo);
   nqb_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));

@@ -143,13 +143,16 @@ class _RadialMLPGemmFn(torch.autograd.Function):
     def forward(ctx, emb, w1s, fwd: ops.GroupedGemm, bwd: ops.GroupedGemm, W: int):
         E, hid = emb.shape[0], w1s.shape[1]
         fast = emb.shape[1] == 8 and hid == 128  # fused CUDA-core kernels for the K = 8 layer
+        h_lo = None
         if fast:
+            # the hidden kernel also writes the tf32 low part of h, so the GEMM's producers only copy
             h = torch.empty((E, hid), dtype=emb.dtype, device=emb.device)
-            ops.mlp_hidden_fwd(emb, w1s, h)
+            h_lo = torch.empty_like(h)
+            ops.mlp_hidden_fwd(emb, w1s, h, h_lo)
         else:
             h = torch.nn.functional.silu(torch.mm(emb, w1s))
         out = torch.empty((E, W), dtype=emb.dtype, device=emb.device)
-        fwd.run(h, out, E)
+        fwd.run(h, out, E, a_lo=h_lo)
         ctx.bwd, ctx.w1s, ctx.fast = bwd, w1s, fast
         ctx.save_for_backward(emb)  # the pre-activation is recomputed in the backward (8 FMAs per value)
         return out

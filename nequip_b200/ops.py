@@ -466,23 +466,28 @@ class GroupedGemm:
         self.descs = torch.tensor(rows, dtype=torch.int64, device=device)
         self.ndesc = len(rows)
 
-    def run(self, a: torch.Tensor, c: torch.Tensor, M: int, rowscale: Optional[torch.Tensor] = None):
+    def run(self, a: torch.Tensor, c: torch.Tensor, M: int, rowscale: Optional[torch.Tensor] = None,
+            a_lo: Optional[torch.Tensor] = None):
+        """``a_lo``: optional pre-split low parts of ``a`` (same shape/strides; see ``mlp_hidden_fwd``)."""
         _require_cuda(a, c)
         if a.dtype != torch.float32 or c.dtype != torch.float32:
             raise TypeError("GroupedGemm.run: float32 only")
+        if a_lo is not None and (a_lo.dtype != torch.float32 or a_lo.shape != a.shape or a_lo.stride() != a.stride()):
+            raise ValueError("GroupedGemm.run: a_lo must match a")
         _capi.check(
-            _capi.lib().nqb_gemm_grouped(_ptr(self.descs), self.ndesc, self.ntiles_total, _ptr(a), _ptr(self.prepared),
-                                         _ptr(c), _ptr(rowscale), (int(rowscale.shape[-1]) if rowscale is not None else 0), int(M), _stream()),
+            _capi.lib().nqb_gemm_grouped(_ptr(self.descs), self.ndesc, self.ntiles_total, _ptr(a), _ptr(a_lo),
+                                         _ptr(self.prepared), _ptr(c), _ptr(rowscale),
+                                         (int(rowscale.shape[-1]) if rowscale is not None else 0), int(M), _stream()),
             "nqb_gemm_grouped",
         )
         return c
 
 
-def mlp_hidden_fwd(emb: torch.Tensor, w1s: torch.Tensor, h: torch.Tensor) -> None:
-    """``h = silu(emb @ w1s)`` ([E,8] x [8,128])."""
+def mlp_hidden_fwd(emb: torch.Tensor, w1s: torch.Tensor, h: torch.Tensor, h_lo: Optional[torch.Tensor] = None) -> None:
+    """``h = silu(emb @ w1s)`` ([E,8] x [8,128]); ``h_lo`` (optional) receives the tf32 low part of ``h``."""
     _require_cuda(emb, w1s, h)
     _capi.check(_capi.lib().nqb_mlp_hidden_fwd(_ptr(emb), _ptr(w1s), emb.shape[0], emb.shape[1], w1s.shape[1], _ptr(h),
-                                               _stream()), "nqb_mlp_hidden_fwd")
+                                               _ptr(h_lo), _stream()), "nqb_mlp_hidden_fwd")
 
 
 def mlp_hidden_bwd(emb: torch.Tensor, w1s: torch.Tensor, gh: torch.Tensor, gemb: torch.Tensor) -> None:

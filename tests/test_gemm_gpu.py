@@ -94,6 +94,37 @@ def test_mlp_hidden_layer_kernels(E):
     ops.mlp_hidden_bwd(emb.cuda(), w1s.cuda(), gh.cuda(), ge)
     torch.testing.assert_close(h.cpu().double(), h_ref.detach(), atol=2e-6, rtol=2e-6)
     torch.testing.assert_close(ge.cpu().double(), ge_ref, atol=2e-5, rtol=2e-5)
+    # optional second output: the tf32 low part of h, bit-exact against the integer formula
+    h2, h_lo = torch.empty(E, 128, device="cuda"), torch.empty(E, 128, device="cuda")
+    ops.mlp_hidden_fwd(emb.cuda(), w1s.cuda(), h2, h_lo)
+    assert torch.equal(h2, h)
+    assert torch.equal(h_lo, _tf32_lo(h))
+
+
+def _tf32_lo(a):
+    """rna_tf32(a - trunc_tf32(a)): what the tensor core does not see of an fp32 operand."""
+    hi = (a.view(torch.int32) & -8192).view(torch.float32)
+    lo = a - hi
+    return ((lo.view(torch.int32) + 4096) & -8192).view(torch.float32)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("M,K,N", [(300, 64, 64), (1000, 128, 864), (4099, 1728, 128), (260, 100, 36)])
+def test_presplit_low_parts_give_the_same_result(M, K, N):
+    """Handing the kernel pre-split low parts of A (as the hidden-layer kernel produces them) must give
+    bit-identical output to letting it derive them."""
+    g = torch.Generator().manual_seed(7 * M + K + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(K, N, generator=g)
+    gg = ops.GroupedGemm([ops.GemmProblem(0, K, 0, N, B)], "cuda")
+    C1 = torch.full((M, N), float("nan"), device="cuda")
+    C2 = torch.full((M, N), float("nan"), device="cuda")
+    gg.run(A, C1, M)
+    gg.run(A, C2, M, a_lo=_tf32_lo(A))
+    torch.cuda.synchronize()
+    assert torch.equal(C1, C2)
+    ref = A.double().cpu() @ B.double()
+    assert (C2.cpu().double() - ref).abs().max().item() <= 1.5e-6 * ref.abs().max().item() + 1e-7
 
 
 @pytest.mark.timeout(120)
