@@ -40,7 +40,7 @@ WORKLOADS = {
     "asi_50k_l3_f32": ("asi", 37, dict(l_max=3, num_layers=5, num_features=32, radial_mlp_depth=1, radial_mlp_width=128)),
     "tiny": ("water", 5, dict(l_max=2, num_layers=3, num_features=8, radial_mlp_depth=1, radial_mlp_width=16)),
 }
-CPU_SAMPLE_NSIDE = {"li3po4_10k_l2_f64": 9, "water_1k_l2_f32": 8, "asi_50k_l3_f32": 9, "tiny": 4}
+CPU_SAMPLE_NSIDE = {"li3po4_10k_l2_f64": 7, "water_1k_l2_f32": 8, "asi_50k_l3_f32": 9, "tiny": 4}
 R_MAX = 5.0
 
 
@@ -118,6 +118,31 @@ def build_system(workload, seed, n_side=None):
     return sysd, meta, mk
 
 
+def pick_threads(workload):
+    """Thread count for the CPU arm: torch's intra-op pool oversubscribes badly on many-core hosts (128
+    threads were 12x slower than 8 on the first GPU box), so time one small step at a few counts and keep
+    the fastest.  Returns (threads, {count: seconds})."""
+    from nequip_b200.nn.model import NequIPEnergyModel
+    from oracle import model as omodel
+
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    sysd, meta, mk = build_system(workload, seed=0, n_side=5)
+    model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
+                              avg_num_neighbors=meta["avg_num_neighbors"], **mk)
+    sd, cfg = model.state_dict(), model.config
+    times = {}
+    for c in cands:
+        torch.set_num_threads(c)
+        omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=20000)
+        t0 = time.perf_counter()
+        omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=20000)
+        times[c] = time.perf_counter() - t0
+    best = min(times, key=times.get)
+    torch.set_num_threads(best)
+    return best, times
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's own (e3nn-formulation) CPU implementation of the path -- the
     oracle port -- with all host threads, on a bounded sample of the workload."""
@@ -126,8 +151,7 @@ def run_reference(args, rank, world):
     from nequip_b200.nn.model import NequIPEnergyModel
     from oracle import model as omodel
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores, _ = pick_threads(args.workload)
     ns = CPU_SAMPLE_NSIDE[args.workload]
     sysd, meta, mk = build_system(args.workload, seed=0, n_side=ns)
     model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
@@ -142,7 +166,8 @@ def run_reference(args, rank, world):
         omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=chunk)
     dt = (time.perf_counter() - t0) / args.steps
     val = n_atoms / dt
-    sample = f"{n_atoms}-atom {WORKLOADS[args.workload][0]} box, same model/density, E={sysd['edge_index'].shape[1]}, edge chunk {chunk}"
+    sample = (f"{n_atoms}-atom {WORKLOADS[args.workload][0]} box, same model/density, E={sysd['edge_index'].shape[1]}, "
+              f"edge chunk {chunk}, {cores} of {os.cpu_count()} host threads (fastest of a short sweep)")
     line = {
         "impl": "reference", "metric": "atom-steps/sec (energy+forces)", "value": val, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -158,8 +183,7 @@ def cpu_baseline(workload):
     from nequip_b200.nn.model import NequIPEnergyModel
     from oracle import model as omodel
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores, _ = pick_threads(workload)
     ns = CPU_SAMPLE_NSIDE[workload]
     sysd, meta, mk = build_system(workload, seed=0, n_side=ns)
     model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
@@ -174,7 +198,8 @@ def cpu_baseline(workload):
         reps += 1
     dt = (time.perf_counter() - t0) / reps
     return {"value": n_atoms / dt, "unit": "atom-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n_atoms}-atom {WORKLOADS[workload][0]} box (same model, density, r_max), {reps} steps, E={sysd['edge_index'].shape[1]}"}
+            "sample": (f"{n_atoms}-atom {WORKLOADS[workload][0]} box (same model, density, r_max), {reps} steps, "
+                       f"E={sysd['edge_index'].shape[1]}, {cores} of {os.cpu_count()} host threads (fastest of a short sweep)")}
 
 
 def main():

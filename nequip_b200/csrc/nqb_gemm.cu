@@ -55,10 +55,10 @@ constexpr int TM = 128;          // rows per tile
 constexpr int TN = 128;          // max columns per tile
 constexpr int KC = 32;           // K chunk
 #ifndef NQB_KH
-#define NQB_KH 16
-#define NQB_RAW 5
-#define NQB_NLO 5
-#define NQB_DEPTH 3
+#define NQB_KH 32
+#define NQB_RAW 3
+#define NQB_NLO 2
+#define NQB_DEPTH 2
 #endif
 constexpr int KH = NQB_KH;       // A is staged in pieces of KH k (16 or 32 = half or whole weight chunk)
 constexpr int RAW = NQB_RAW;     // ring of raw A pieces (TM x KH fp32), filled by cp.async
@@ -66,14 +66,18 @@ constexpr int DEPTH = NQB_DEPTH; // pieces in flight per CTA
 constexpr int NLO = NQB_NLO;     // ring of A low-part pieces
 constexpr int HPC = 32 / KH;     // pieces per weight chunk
 static_assert(KH == 16 || KH == 32, "KH");
-static_assert(DEPTH <= RAW - 1, "ring depth");
-constexpr bool PRESPLIT_OK = NLO >= RAW;  // pre-split mode refills both rings at the same distance
+constexpr bool PRESPLIT_OK = true;
 constexpr int BSLOTS = 4;        // B slots: a ring when K > 128, resident per N-tile when K <= 128
 constexpr int SEG_H = 320 / KH;  // pieces per accumulation segment (40 accumulate steps on the hi*hi accumulator)
+#ifndef NQB_NPG
+#define NQB_NPG 1
+#endif
 constexpr int NPW = 4;            // producer warps
+constexpr int NPG = NQB_NPG;      // independent producer groups (pieces are dealt round-robin)
+static_assert(DEPTH * NPG <= RAW - 1, "a group refills the stage of an already consumed piece");
+static_assert(NLO >= 2 && NPW % NPG == 0, "rings");
 constexpr int NPROD = NPW * 32;   // producer threads
 constexpr int NTHREADS = NPROD + 256;  // + epilogue warpgroup + {loader, MMA, 2 idle} warps
-constexpr int RG = TM / NPW / 8;  // 8-row groups per producer warp
 constexpr int BLOCK_FLOATS = 2 * TN * KC;  // one prepared weight block: [hi | lo] x [128 x 32]
 
 struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
@@ -84,8 +88,8 @@ struct GemmDesc {  // mirrored by nequip_b200/ops.py (int64 fields)
 };
 
 struct Smem {
-  float araw[RAW][TM * KH];        // 5 x 8 KB: fp32 A pieces, canonical K-major core-matrix layout
-  float alo[NLO][TM * KH];         // 5 x 8 KB: their tf32 low parts
+  float araw[RAW][TM * KH];        // 3 x 16 KB: fp32 A pieces, canonical K-major core-matrix layout
+  float alo[NLO][TM * KH];         // 2 x 16 KB: their tf32 low parts
   float b[BSLOTS][BLOCK_FLOATS];   // 4 x 32 KB
   float stage[4][32 * 32];         // epilogue staging, one 32x32 tile per warp (swizzled)
   uint64_t a_full[RAW], a_done[RAW];
@@ -147,7 +151,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   const int64_t mtiles = (M + TM - 1) / TM;
 
   if (tid == 0) {
-    for (int s = 0; s < RAW; ++s) { mbar_init(&S.a_full[s], NPROD); mbar_init(&S.a_done[s], 1); }
+    for (int s = 0; s < RAW; ++s) { mbar_init(&S.a_full[s], NPROD / NPG); mbar_init(&S.a_done[s], 1); }
     for (int s = 0; s < BSLOTS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 128); }
     fence_barrier_init();
@@ -163,16 +167,23 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   // partial sums in registers (232), producers, loader and MMA warps need few
   if (warp < NPW) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    // =========================== A producer =========================================================
-    // cp.async (16 bytes = one core-matrix row) global -> raw ring, DEPTH half-chunks ahead across work-item
-    // boundaries.  The fp32 tile itself is the tf32 high operand (the tensor core ignores the low 13
-    // mantissa bits); each thread then reads back ITS OWN pieces and writes lo = a - trunc_tf32(a).
-    // (Register prefetching was stuck at ~7 B/clk/SM no matter how many loads were nominally in flight,
-    // profiles/r01_gemm_roles.txt.)
-    // thread -> rows warp*32 + g*8 + r8 (g < 4), k-group kq: 4 x 16 bytes per half-chunk
+    // =========================== A producers ========================================================
+    // NPG independent groups of NPW / NPG warps; group g owns the pieces i = g (mod NPG) of the CTA's flat
+    // piece sequence, so the latency chains of consecutive pieces (copy -> read back -> split -> fence ->
+    // arrive -> wait for a free stage -> next copy) overlap instead of adding up.
+    // Per owned piece: cp.async (16 bytes = one core-matrix row) global -> raw stage, DEPTH own pieces ahead
+    // and across work-item boundaries.  The fp32 tile itself is the tf32 high operand (the tensor core
+    // ignores the low 13 mantissa bits); each thread then reads back ITS OWN 16-byte pieces and writes
+    // lo = rna_tf32(a - trunc_tf32(a)).  (Register prefetching was stuck at ~7 B/clk/SM no matter how many
+    // loads were nominally in flight, profiles/r01_gemm_roles.txt.)
+    // thread -> rows gw*(8 RG) + g*8 + r8 (g < RG), k-groups kh*4 + kq
+    constexpr int WPG = NPW / NPG;          // warps per group
+    constexpr int RG = TM / WPG / 8;        // 8-row groups per warp
+    constexpr int KQ = KH / 16;             // 16-k halves per piece
+    const int grp = warp / WPG, gw = warp % WPG;
     const int r8 = lane & 7, kq = lane >> 3;
     PROF_DECL
-    // cursor over the CTA's flat sequence of (N-tile q, M-tile mt, half-chunk h)
+    // cursor over the CTA's flat sequence of (N-tile q, M-tile mt, piece h); n = index of the cursor's piece
     int pq = sch.q, ph_ = 0, pnh = 1, pK = 0;
     int64_t pmt = sch.m_start, plda = 0;
     const float* pA = nullptr;
@@ -189,16 +200,28 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
       pK = w.K;
     };
     if (pvalid) open_q();
-    uint32_t n_issued = 0;
-    const int my_off = (warp * 4) * (KH / 4 * 32) + kq * 32 + r8 * 4;  // float offset of piece (g = 0, kh = 0)
-    constexpr int KQ = KH / 16;  // 16-k halves per piece: k-group = kh * 4 + kq
-    auto issue = [&]() {  // cp.async the cursor's piece (if any) into its raw stage, advance, commit
+    auto advance = [&]() {
+      if (++ph_ == pnh) {
+        ph_ = 0;
+        pmt += sch.m_step;
+        if (pmt >= mtiles) {
+          pmt = sch.m_start;
+          pq += sch.q_step;
+          pvalid = pq < sch.nq_total;
+          if (pvalid) open_q();
+        }
+      }
+    };
+    uint32_t n = 0, own_issued = 0;
+    for (int j = 0; j < grp && pvalid; ++j) { advance(); ++n; }  // first own piece
+    const int my_off = (gw * RG) * (KH / 4 * 32) + kq * 32 + r8 * 4;  // float offset of piece (g = 0, kh = 0)
+    auto issue = [&]() {  // cp.async the cursor's (own) piece into its stage, move to the next own piece, commit
       if (pvalid) {
-        float* dst = S.araw[n_issued % RAW] + my_off;
-        float* dlo = S.alo[n_issued % NLO] + my_off;
+        float* dst = S.araw[n % RAW] + my_off;
+        float* dlo = S.alo[n % NLO] + my_off;
 #pragma unroll
         for (int g = 0; g < RG; ++g) {
-          const int64_t m = pmt * TM + warp * 32 + g * 8 + r8;
+          const int64_t m = pmt * TM + gw * (8 * RG) + g * 8 + r8;
 #pragma unroll
           for (int kh = 0; kh < KQ; ++kh) {
             const int k = ph_ * KH + (kh * 4 + kq) * 4;
@@ -210,50 +233,48 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
             if (presplit) cp_async16(dlo + g * (KH / 4 * 32) + kh * 128, pAlo + off, in ? 16u : 0u);
           }
         }
-        ++n_issued;
-        if (++ph_ == pnh) {
-          ph_ = 0;
-          pmt += sch.m_step;
-          if (pmt >= mtiles) {
-            pmt = sch.m_start;
-            pq += sch.q_step;
-            pvalid = pq < sch.nq_total;
-            if (pvalid) open_q();
-          }
-        }
+        ++own_issued;
+#pragma unroll 1
+        for (int j = 0; j < NPG && pvalid; ++j) { advance(); ++n; }
       }
       cp_async_commit();
     };
 #pragma unroll 1
     for (int j = 0; j < DEPTH; ++j) issue();
 #pragma unroll 1
-    for (uint32_t i = 0; i < n_issued; ++i) {
-      PROF_WAIT(1, cp_async_wait<DEPTH - 1>())  // my pieces of half-chunk i have landed
+    for (uint32_t k = 0; k < own_issued; ++k) {
+      const uint32_t i = grp + k * NPG;  // global index of this own piece
+      PROF_WAIT(1, cp_async_wait<DEPTH - 1>())  // my parts of piece i have landed
 #ifndef NQB_X_NOLO
       if (!presplit) {
         // lo stage i % NLO was read by the MMAs of piece i - NLO
         if (i >= NLO) PROF_WAIT(0, mbar_wait(&S.a_done[(i - NLO) % RAW], ((i - NLO) / RAW) & 1))
         const float* raw = S.araw[i % RAW] + my_off;
         float* lo = S.alo[i % NLO] + my_off;
-        float4 a[RG * KQ];
 #pragma unroll
-        for (int g = 0; g < RG; ++g)
+        for (int g0 = 0; g0 < RG; g0 += 4) {
+          float4 a[4 * KQ];
 #pragma unroll
-          for (int kh = 0; kh < KQ; ++kh) a[g * KQ + kh] = *reinterpret_cast<const float4*>(raw + g * (KH / 4 * 32) + kh * 128);
+          for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int g = 0; g < RG; ++g)
+            for (int kh = 0; kh < KQ; ++kh)
+              a[g * KQ + kh] = *reinterpret_cast<const float4*>(raw + (g0 + g) * (KH / 4 * 32) + kh * 128);
 #pragma unroll
-          for (int kh = 0; kh < KQ; ++kh) {
-            const float4 t = a[g * KQ + kh];
-            *reinterpret_cast<float4*>(lo + g * (KH / 4 * 32) + kh * 128) =
-                make_float4(tf32_lo(t.x), tf32_lo(t.y), tf32_lo(t.z), tf32_lo(t.w));
-          }
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int kh = 0; kh < KQ; ++kh) {
+              const float4 t = a[g * KQ + kh];
+              *reinterpret_cast<float4*>(lo + (g0 + g) * (KH / 4 * 32) + kh * 128) =
+                  make_float4(tf32_lo(t.x), tf32_lo(t.y), tf32_lo(t.z), tf32_lo(t.w));
+            }
+        }
       }
 #endif
       PROF_WAIT(2, fence_proxy_async(); mbar_arrive(&S.a_full[i % RAW]))
-      // raw stage (i + DEPTH) % RAW was last read by the MMAs of piece i + DEPTH - RAW
-      if (i + DEPTH >= RAW)
-        PROF_WAIT(0, mbar_wait(&S.a_done[(i + DEPTH - RAW) % RAW], ((i + DEPTH - RAW) / RAW) & 1))
+      // the next own piece to load, j = i + DEPTH * NPG, reuses the stages of pieces j - RAW and j - NLO
+      const uint32_t j = i + DEPTH * NPG;
+      if (j >= RAW) PROF_WAIT(0, mbar_wait(&S.a_done[(j - RAW) % RAW], ((j - RAW) / RAW) & 1))
+      if (presplit && NLO != RAW && j >= NLO) mbar_wait(&S.a_done[(j - NLO) % RAW], ((j - NLO) / RAW) & 1);
       issue();
     }
     cp_async_wait<0>();
@@ -417,7 +438,8 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
     constexpr uint32_t A_STAGE = (TM * KH * sizeof(float)) >> 4;
     constexpr uint32_t B_SLOT = (BLOCK_FLOATS * sizeof(float)) >> 4, B_LO = (TN * KC * sizeof(float)) >> 4;
     constexpr uint32_t B_HALF = (KH / 4 * 128) >> 4;  // the second piece of a weight chunk (KH = 16)
-    uint32_t it = 0, gseg = 0, bit = 0;
+    uint32_t gseg = 0, bit = 0;
+    uint32_t s = 0, ph = 0, s_lo = 0;  // raw ring stage + phase, lo ring stage of the next piece
     uint32_t bpar = 0;  // per-slot bit: parity of the loads consumed (waited for)
     PROF_DECL
     for (int q = sch.q; q < sch.nq_total; q += sch.q_step) {
@@ -435,8 +457,8 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
           const uint32_t d_hh = tmem + buf * 256, d_x = d_hh + 128;
           uint32_t fresh = 1;  // the first half-chunk of a segment overwrites the accumulators
           const int h1 = min(w.nh, h0 + SEG_H);
-          for (int h = h0; h < h1; ++h, ++it) {
-            const uint32_t s = it % RAW, ph = (it / RAW) & 1, half = h % HPC;
+          for (int h = h0; h < h1; ++h) {
+            const uint32_t half = h % HPC;
             if (!half) {  // first piece of a weight chunk
               if (w.resident) {
                 slot = h / HPC;
@@ -448,10 +470,10 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
                 bpar ^= 1u << slot;
               }
             }
-            PROF_WAIT(2, mbar_wait(&S.a_full[s], ph))
-            tc_fence_after();
-            const uint64_t a_hi = dR0 + (uint64_t)(s * A_STAGE), a_lo = dL0 + (uint64_t)((it % NLO) * A_STAGE);
+            const uint64_t a_hi = dR0 + (uint64_t)(s * A_STAGE), a_lo = dL0 + (uint64_t)(s_lo * A_STAGE);
             const uint64_t b_hi = dB0 + (uint64_t)(slot * B_SLOT + half * B_HALF), b_lo = b_hi + B_LO;
+            // (the stage was filled through the generic proxy and fenced by the producers: no tcgen05 fence)
+            PROF_WAIT(2, mbar_wait(&S.a_full[s], ph))
             if (leader) {
 #ifndef NQB_X_NOMMA
               // k-step advance = 2 core matrices = 256 bytes = 16 descriptor units.  MMAs on the same
@@ -485,7 +507,8 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
               if (!w.resident && (half == HPC - 1 || h == w.nh - 1)) umma_commit(&S.b_empty[slot]);
             }
             fresh = 0;
-            __syncwarp();
+            if (++s == RAW) { s = 0; ph ^= 1; }
+            if (++s_lo == NLO) s_lo = 0;
           }
           if (leader) umma_commit(&S.acc_full[buf]);
           __syncwarp();
