@@ -100,6 +100,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the largest captured launch of ``kernel`` from the committed
+    ``ncu --set full`` summary (profiles/r01_ncu_full_summary.json, written from gpurun_out/final_*.raw.csv)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    try:
+        rows = json.load(open(p))[kernel]
+        r = max(rows, key=lambda x: x["ms"])
+        return int(round((r["dram_read_GB"] + r["dram_write_GB"]) * 1e9))
+    except Exception:
+        return None
+
+
 def tp_algorithmic_bytes(sig, N, E, elem=4, backward=False):
     """forward reads x, edge_attr, edge_weight, two int64 index arrays, writes out."""
     b = elem * (N * sig.d_in + E * sig.s_dim + E * sig.weight_numel + N * sig.d_out) + 16 * E
@@ -408,7 +420,8 @@ def main():
         k_ms = e0.elapsed_time(e1) / reps
         alg = tp_algorithmic_bytes(sig, n_atoms, n_edges)
         ach = alg / (k_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic("tp_fwd2_kernel"),  # dram read+write bytes per launch (ncu --set full), or None
                 "kernel": "tp_fwd_kernel<float> (fused TP+scatter forward)", "layer_signature_W": sig.weight_numel,
                 "alg_bytes_per_launch": alg, "ms_per_launch": k_ms, "peak_source": peak_src,
                 "inputs": "w stream %.2f GB >> 126 MB L2" % (n_edges * sig.weight_numel * 4 / 1e9)}
