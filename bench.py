@@ -443,7 +443,7 @@ def main():
         algb = tp_algorithmic_bytes(sig, n_atoms, n_edges, backward=True)
         roof["backward"] = {"ms_per_launch": b_ms, "alg_bytes_per_launch": algb,
                             "achieved": algb / (b_ms * 1e-3) / 1e9, "frac": algb / (b_ms * 1e-3) / 1e9 / peak,
-                            "note": "includes torch.zeros_like for grad_x/grad_y"}
+                            "traffic": ncu_traffic("tp_bwd2_kernel"), "note": "includes torch.zeros_like for grad_x/grad_y"}
         del x, y, w, xg, yg, wg, out, go
 
     cpu = None

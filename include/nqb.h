@@ -156,14 +156,31 @@ int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const float* grad_h, 
  *    tile0 (prefix sum of ntiles), flags (bit0: accumulate into C)};  offsets in floats from the bases.
  * Requirements: K, N, lda, ldc, a_off, c_off multiples of 4; bases 16-byte aligned.
  * B_p is prepared once (split hi/lo, tiled) with nqb_gemm_prepare into nqb_gemm_prepared_floats(K,N) floats.
+ * tile_ctas_dev (nullable): int32 {first CTA, CTAs} per N-tile -- a cost-weighted split of sched_ctas CTAs over
+ * the N-tiles computed by the host (problems of one launch differ in K, N and store mode); used when
+ * sched_ctas <= #SMs, otherwise the even split is used.
  * a_lo_base (nullable): pre-split low parts of A, same offsets/strides as a_base (see nqb_mlp_hidden_fwd);
  * when null the kernel derives them itself. */
 int64_t nqb_gemm_prepared_floats(int K, int N);
 int nqb_gemm_prepare(const float* B, int64_t ldb, int K, int N, int transposed, float scale, float* prepared,
                      nqb_stream_t st);
-int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const float* a_base,
+int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const int32_t* tile_ctas_dev,
+                     int sched_ctas, const float* a_base,
                      const float* a_lo_base, const float* prepared_base, float* c_base,
                      const float* rowscale_base, int64_t rs_ld, int64_t M, nqb_stream_t st);
+
+/* Gate nonlinearity (e3nn nn.Gate with normalize2mom'd SiLU for even / tanh for odd scalars and gates,
+ * nequip/nn/convnetlayer.py:42-56,104-112), one kernel per direction.  Column tables (device, int32) are
+ * built by the host from the irreps, for either layout:
+ *   forward, per OUTPUT column j: src[j], gate[j] (-1: scalar), kind[j] (0 silu, 1 tanh):
+ *     out[n,j] = gate[j] < 0 ? act(x[n,src[j]]) : x[n,src[j]] * act(x[n,gate[j]])
+ *   backward, per INPUT column i: tab[6*i..] = {role, a, b, c, d, kind}
+ *     role 0 scalar (a = output column); role 1 gated value (a = output column, b = gate input column);
+ *     role 2 gate (a = first output column, b = first gated input column, c = component stride, d = 2l+1). */
+int nqb_gate_fwd(int dtype, const void* x, int64_t N, int d_in, int d_out, const int32_t* src,
+                 const int32_t* gate, const int32_t* kind, void* out, nqb_stream_t st);
+int nqb_gate_bwd(int dtype, const void* x, const void* grad_out, int64_t N, int d_in, int d_out,
+                 const int32_t* tab, void* grad_x, nqb_stream_t st);
 
 /* number of kernels the library has launched in this process (bench accounting) */
 int64_t nqb_launch_count(void);

@@ -112,8 +112,18 @@ __device__ __forceinline__ const GemmDesc* find_desc(const GemmDesc* d, int nd, 
 struct Sched {
   int q, q_step, nq_total;
   int64_t m_start, m_step;
-  __device__ Sched(int b, int G, int T) {
-    if (T <= G) {
+  // tile_ctas (nullable): per N-tile {first CTA, number of CTAs} of a cost-weighted split computed by the
+  // host for a grid of exactly sched_ctas CTAs (problems of one launch differ in K, N and store mode, so
+  // an even split leaves most CTAs idle while the expensive tiles finish)
+  __device__ Sched(int b, int G, int T, const int32_t* tile_ctas, int sched_ctas) {
+    nq_total = T;
+    if (tile_ctas != nullptr && G == sched_ctas) {
+      q = T; q_step = T; m_start = 0; m_step = 1;
+      for (int t = 0; t < T; ++t) {
+        const int c0 = tile_ctas[2 * t], n = tile_ctas[2 * t + 1];
+        if (b >= c0 && b < c0 + n) { q = t; m_start = b - c0; m_step = n; break; }
+      }
+    } else if (T <= G) {
       const int R = G / T;
       q = (b < T * R) ? (b % T) : T;  // T = no work
       q_step = T;
@@ -122,7 +132,6 @@ struct Sched {
     } else {
       q = b; q_step = G; m_start = 0; m_step = 1;
     }
-    nq_total = T;
   }
 };
 
@@ -142,7 +151,8 @@ __device__ __forceinline__ void decode_q(const GemmDesc* descs, int ndesc, int q
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const float* __restrict__ a_base,
+k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const int32_t* __restrict__ tile_ctas,
+         int sched_ctas, const float* __restrict__ a_base,
          const float* __restrict__ a_lo_base, const float* __restrict__ b_base, float* __restrict__ c_base, const float* __restrict__ rs_base, int64_t rs_ld,
          int64_t M) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -161,7 +171,7 @@ k_gemm3x(const GemmDesc* __restrict__ descs, int ndesc, int ntiles_total, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
-  const Sched sch(blockIdx.x, gridDim.x, ntiles_total);
+  const Sched sch(blockIdx.x, gridDim.x, ntiles_total, tile_ctas, sched_ctas);
 
   // register budget per warpgroup (launch: 65536 / 384 = 168 each): the epilogue keeps a 128-value row of
   // partial sums in registers (232), producers, loader and MMA warps need few
@@ -589,7 +599,8 @@ extern "C" int nqb_gemm_prepare(const float* B, int64_t ldb, int K, int N, int t
   return 0;
 }
 
-extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const float* a_base,
+extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const int32_t* tile_ctas_dev,
+                                int sched_ctas, const float* a_base,
                                 const float* a_lo_base, const float* prepared_base, float* c_base,
                                 const float* rowscale_base, int64_t rs_ld, int64_t M, nqb_stream_t st) {
   if (ndesc <= 0 || ntiles_total <= 0) return nqb_set_error("nqb_gemm_grouped: empty problem list");
@@ -603,8 +614,10 @@ extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_tot
     attr_set = true;
   }
   const int64_t nwork = ((M + TM - 1) / TM) * (int64_t)ntiles_total;
-  const int grid = (int)(nwork < gemm_sm_count() ? nwork : gemm_sm_count());
-  k_gemm3x<<<grid, 384, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, a_base, a_lo_base,
+  int grid = (int)(nwork < gemm_sm_count() ? nwork : gemm_sm_count());
+  if (tile_ctas_dev != nullptr && sched_ctas > 0 && sched_ctas <= gemm_sm_count()) grid = sched_ctas;
+  else tile_ctas_dev = nullptr;
+  k_gemm3x<<<grid, 384, sizeof(Smem) + 1024, (cudaStream_t)st>>>((const GemmDesc*)descs_dev, ndesc, ntiles_total, tile_ctas_dev, sched_ctas, a_base, a_lo_base,
                                                                  prepared_base, c_base, rowscale_base, rs_ld, M);
   nqb_count_launch();
   cudaError_t e = cudaGetLastError();

@@ -245,12 +245,21 @@ class Gate(torch.nn.Module):
         self.irreps_in = self.irreps_scalars + self.irreps_gates + self.irreps_gated
         gp = self.irreps_gates[0][1].p if len(self.irreps_gates) else 1
         self.irreps_out = self.irreps_scalars + Irreps([(m, Irrep(ir.l, ir.p * gp)) for m, ir in self.irreps_gated])
+        self.use_fused = True  # CUDA: fused kernels; the torch formulation below is the readable definition
+        self._tabs = None
 
     @staticmethod
     def _act(x, p: int):
         return torch.nn.functional.silu(x) * C_SILU if p == 1 else torch.tanh(x) * C_TANH
 
     def forward(self, x):
+        if x.is_cuda and self.use_fused:
+            # one kernel per direction (nqb_gate_fwd/bwd) instead of ~30 strided elementwise ops
+            key = (x.device, self.layout)
+            if self._tabs is None or self._tabs[0] != key:
+                self._tabs = (key, ops.GateTables(self.irreps_scalars, self.irreps_gates, self.irreps_gated,
+                                                  self.layout, x.device))
+            return ops.gate(x, self._tabs[1])
         N = x.shape[0]
         ns, ng = self.irreps_scalars.dim, self.irreps_gates.dim
         parts = []

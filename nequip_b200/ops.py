@@ -462,9 +462,37 @@ class GroupedGemm:
             b_off += nfl
             tile0 += ntiles
         self.ntiles_total = tile0
+        self.tile_ctas, self.sched_ctas = self._weighted_split(rows, device)
         self.prepared = torch.cat(blobs)
         self.descs = torch.tensor(rows, dtype=torch.int64, device=device)
         self.ndesc = len(rows)
+
+    @staticmethod
+    def _weighted_split(rows, device):
+        """CTAs per N-tile proportional to the tile's cost (pieces of K to multiply + columns to store, reduce-adds
+        twice a store), for a grid of one CTA per SM.  None when there are more N-tiles than SMs."""
+        if torch.device(device).type != "cuda":
+            return None, 0
+        G = torch.cuda.get_device_properties(device).multi_processor_count
+        cost = []
+        for (_a, _c, _b, _rs, _lda, _ldc, K, N, _kch, ntiles, _t0, flags) in rows:
+            for t in range(ntiles):
+                ncols = min(128, N - t * 128)
+                cost.append(((K + 31) // 32) * 1000.0 + ((ncols + 31) // 32) * 650.0 * (2.0 if flags & 5 else 1.0))
+        T = len(cost)
+        # uniform launches (the radial-MLP GEMMs) keep the even split: its CTAs sweep the M-tiles in lockstep
+        # and share every A tile in L2
+        if T > G or T < 2 or max(cost) < 1.3 * min(cost):
+            return None, 0
+        n = [1] * T
+        for _ in range(G - T):  # give the next CTA to the tile with the largest per-CTA load
+            i = max(range(T), key=lambda j: cost[j] / n[j])
+            n[i] += 1
+        tab, c0 = [], 0
+        for j in range(T):
+            tab += [c0, n[j]]
+            c0 += n[j]
+        return torch.tensor(tab, dtype=torch.int32, device=device), c0
 
     def run(self, a: torch.Tensor, c: torch.Tensor, M: int, rowscale: Optional[torch.Tensor] = None,
             a_lo: Optional[torch.Tensor] = None):
@@ -475,7 +503,8 @@ class GroupedGemm:
         if a_lo is not None and (a_lo.dtype != torch.float32 or a_lo.shape != a.shape or a_lo.stride() != a.stride()):
             raise ValueError("GroupedGemm.run: a_lo must match a")
         _capi.check(
-            _capi.lib().nqb_gemm_grouped(_ptr(self.descs), self.ndesc, self.ntiles_total, _ptr(a), _ptr(a_lo),
+            _capi.lib().nqb_gemm_grouped(_ptr(self.descs), self.ndesc, self.ntiles_total, _ptr(self.tile_ctas),
+                                         int(self.sched_ctas), _ptr(a), _ptr(a_lo),
                                          _ptr(self.prepared), _ptr(c), _ptr(rowscale),
                                          (int(rowscale.shape[-1]) if rowscale is not None else 0), int(M), _stream()),
             "nqb_gemm_grouped",
@@ -495,3 +524,83 @@ def mlp_hidden_bwd(emb: torch.Tensor, w1s: torch.Tensor, gh: torch.Tensor, gemb:
     _require_cuda(emb, w1s, gh, gemb)
     _capi.check(_capi.lib().nqb_mlp_hidden_bwd(_ptr(emb), _ptr(w1s), _ptr(gh), emb.shape[0], emb.shape[1], w1s.shape[1],
                                                _ptr(gemb), _stream()), "nqb_mlp_hidden_bwd")
+
+
+# ---------------------------------------------------------------------------------------
+# Gate nonlinearity -- nqb_gate_fwd / nqb_gate_bwd
+# ---------------------------------------------------------------------------------------
+class GateTables:
+    """Column tables of the fused Gate kernels for ``irreps_in = scalars + gates + gated`` in ``layout``
+    (e3nn ``nn.Gate``, nequip/nn/convnetlayer.py:104-112).  ``p`` of a scalar/gate irrep picks the activation:
+    even -> c_silu * silu, odd -> c_tanh * tanh."""
+
+    def __init__(self, irreps_scalars, irreps_gates, irreps_gated, layout: str, device):
+        from .irreps import Irreps
+
+        sc, ga, gd = Irreps(irreps_scalars), Irreps(irreps_gates), Irreps(irreps_gated)
+        if sum(m for m, _ in ga) != sum(m for m, _ in gd):
+            raise ValueError("Gate: one gate per gated multiplicity")
+        ns, ng = sc.dim, ga.dim
+        self.d_in = ns + ng + gd.dim
+        self.d_out = ns + gd.dim
+        src, gate, kind = [0] * self.d_out, [-1] * self.d_out, [0] * self.d_out
+        tab = [[0] * 6 for _ in range(self.d_in)]
+        off = 0
+        for mul, ir in sc:  # scalars: out[j] = act(x[j])
+            k = 0 if ir.p == 1 else 1
+            for u in range(mul):
+                src[off + u], kind[off + u] = off + u, k
+                tab[off + u] = [0, off + u, 0, 0, 0, k]
+            off += mul
+        gate_kind = []
+        for mul, ir in ga:
+            gate_kind += [0 if ir.p == 1 else 1] * mul
+        g0, in_off, out_off = 0, ns + ng, ns
+        for mul, ir in gd:  # gated chunk: out = x * act(gate of its multiplicity index u)
+            d = ir.dim
+            stride = mul if layout == "ir_mul" else 1  # distance between the 2l+1 components of one u
+            for u in range(mul):
+                gcol, k = ns + g0 + u, gate_kind[g0 + u]
+                first = u if layout == "ir_mul" else u * d
+                tab[gcol] = [2, out_off + first, in_off + first, stride, d, k]
+                for c in range(d):
+                    pos = first + c * stride
+                    src[out_off + pos], gate[out_off + pos], kind[out_off + pos] = in_off + pos, gcol, k
+                    tab[in_off + pos] = [1, out_off + pos, gcol, 0, 0, k]
+            g0 += mul
+            in_off += mul * d
+            out_off += mul * d
+        mk = lambda v: torch.tensor(v, dtype=torch.int32, device=device).contiguous()
+        self.src, self.gate, self.kind = mk(src), mk(gate), mk(kind)
+        self.tab = mk([x for row in tab for x in row])
+
+
+class _GateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, tabs: GateTables):
+        x = x.contiguous()
+        out = torch.empty((x.shape[0], tabs.d_out), dtype=x.dtype, device=x.device)
+        _capi.check(_capi.lib().nqb_gate_fwd(_DT[x.dtype], _ptr(x), x.shape[0], tabs.d_in, tabs.d_out, _ptr(tabs.src),
+                                             _ptr(tabs.gate), _ptr(tabs.kind), _ptr(out), _stream()), "nqb_gate_fwd")
+        ctx.tabs = tabs
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        gx = torch.empty_like(x)
+        t = ctx.tabs
+        _capi.check(_capi.lib().nqb_gate_bwd(_DT[x.dtype], _ptr(x), _ptr(gout), x.shape[0], t.d_in, t.d_out, _ptr(t.tab),
+                                             _ptr(gx), _stream()), "nqb_gate_bwd")
+        return gx, None
+
+
+def gate(x: torch.Tensor, tabs: GateTables) -> torch.Tensor:
+    """Fused Gate nonlinearity on ``x [N, scalars + gates + gated]`` (CUDA, float32/float64)."""
+    _require_cuda(x)
+    if x.dtype not in _DT or x.dim() != 2 or x.shape[1] != tabs.d_in:
+        raise ValueError("gate: x must be [N, %d] float32/float64" % tabs.d_in)
+    return _GateFn.apply(x, tabs)

@@ -144,3 +144,48 @@ def test_neighbor_list_cell_list_vs_bruteforce():
     assert all((j, i, (-a, -b, -c)) in fwd for (i, j, (a, b, c)) in list(fwd)[:2000])
     # sorted by (centre, neighbour)
     assert np.all(np.diff(ei[0]) >= 0)
+
+
+@pytest.mark.parametrize("layout", ["mul_ir", "ir_mul"])
+def test_gate_tables_reproduce_the_torch_gate(layout):
+    """The column tables fed to nqb_gate_fwd/bwd, evaluated in plain torch exactly as the kernels do, must
+    reproduce Gate.forward and its autograd gradient (e3nn nn.Gate semantics, convnetlayer.py:104-112)."""
+    import torch
+
+    from nequip_b200 import ops
+    from nequip_b200.nn.model import C_SILU, C_TANH, Gate
+
+    scal, gates, gated = "8x0e+4x0o", "8x0e+4x0o+4x0e", "8x1o+4x1e+4x2e"
+    g = Gate(scal, gates, gated, layout)
+    t = ops.GateTables(scal, gates, gated, layout, "cpu")
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(5, t.d_in, generator=gen, dtype=torch.float64, requires_grad=True)
+    ref = g(x)
+    go = torch.randn(ref.shape, generator=gen, dtype=torch.float64)
+    (gx_ref,) = torch.autograd.grad(ref, x, go)
+
+    def act(v, k):
+        return torch.where(k == 0, C_SILU * v * torch.sigmoid(v), C_TANH * torch.tanh(v))
+
+    def dact(v, k):
+        s = torch.sigmoid(v)
+        return torch.where(k == 0, C_SILU * s * (1 + v * (1 - s)), C_TANH * (1 - torch.tanh(v) ** 2))
+
+    xd = x.detach()
+    src, gate, kind = t.src.long(), t.gate.long(), t.kind.long()
+    v = xd[:, src]
+    out = torch.where(gate < 0, act(v, kind), v * act(xd[:, gate.clamp(min=0)], kind))
+    torch.testing.assert_close(out, ref.detach(), rtol=1e-12, atol=1e-12)
+    tab = t.tab.view(-1, 6).long()
+    gx = torch.zeros_like(xd)
+    for i in range(t.d_in):
+        role, a, b, c, d, k = (int(z) for z in tab[i])
+        kk = torch.tensor(k)
+        if role == 0:
+            gx[:, i] = go[:, a] * dact(xd[:, i], kk)
+        elif role == 1:
+            gx[:, i] = go[:, a] * act(xd[:, b], kk)
+        else:
+            ssum = sum(go[:, a + cc * c] * xd[:, b + cc * c] for cc in range(d))
+            gx[:, i] = ssum * dact(xd[:, i], kk)
+    torch.testing.assert_close(gx, gx_ref, rtol=1e-12, atol=1e-12)

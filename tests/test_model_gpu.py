@@ -116,3 +116,26 @@ def test_energy_forces_inference_path_tensor_core_mlp(name):
     assert abs(float(e) - float(e_ref)) <= 1e-5 * float(ea_ref.abs().sum()), (float(e), float(e_ref))
     fscale = float(f_ref.abs().max())
     assert float((f - f_ref).abs().max()) <= 5e-5 * fscale, float((f - f_ref).abs().max()) / fscale
+
+
+@pytest.mark.parametrize("layout", ["mul_ir", "ir_mul"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-6)])
+def test_fused_gate_matches_torch_gate(layout, dtype, tol):
+    """nqb_gate_fwd/bwd vs the torch formulation of e3nn's Gate (convnetlayer.py:104-112)."""
+    from nequip_b200.nn.model import Gate
+
+    scal, gates, gated = "64x0e+32x0o", "64x0e+32x0o+32x0e", "64x1o+32x1e+32x2e"
+    g = Gate(scal, gates, gated, layout)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(777, g.irreps_in.dim, generator=gen, dtype=torch.float64)
+    go = torch.randn(777, g.irreps_out.dim, generator=gen, dtype=torch.float64)
+    g.use_fused = False
+    xr = x.clone().requires_grad_(True)
+    ref = g(xr)
+    (gx_ref,) = torch.autograd.grad(ref, xr, go)
+    g.use_fused = True
+    xc = x.to("cuda", dtype).requires_grad_(True)
+    out = g(xc)
+    (gx,) = torch.autograd.grad(out, xc, go.to("cuda", dtype))
+    torch.testing.assert_close(out.detach().cpu().double(), ref.detach(), rtol=tol, atol=tol * 10)
+    torch.testing.assert_close(gx.cpu().double(), gx_ref, rtol=tol * 5, atol=tol * 50)
