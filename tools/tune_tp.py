@@ -20,19 +20,7 @@ VARIANTS = {
     "irmul_b32": GenOptions(layout="ir_mul", acc_cap_bwd=32),
     "irmul_st6": GenOptions(layout="ir_mul", ring_stages=6),
 }
-_OLD = {
-    "nopf": GenOptions(prefetch=False, idx_ahead=False),
-    "pf": GenOptions(prefetch=True, idx_ahead=False),
-    "pf_idx": GenOptions(),
-    "pf_idx_mb4": GenOptions(min_blocks_fwd=4, min_blocks_bwd=3),
-    "pf_idx_a24": GenOptions(acc_cap=24, acc_cap_bwd=16),
-    "pf_idx_a16": GenOptions(acc_cap=16, acc_cap_bwd=12),
-    "nopf_a16": GenOptions(prefetch=False, idx_ahead=False, acc_cap=16, acc_cap_bwd=12),
-    "pf_idx_w2": GenOptions(nwarp=2),
-    "pf_idx_w8": GenOptions(nwarp=8),
-    "pf_idx_nored2": GenOptions(red_v2=False),
-    "nopf_a24_mb": GenOptions(prefetch=False, idx_ahead=False, acc_cap=24, acc_cap_bwd=16, min_blocks_fwd=5, min_blocks_bwd=4),
-}
+# earlier sweeps (register prefetch, accumulator caps, warps per CTA, red.v2): profiles/r01_tune_tp_variants_*.jsonl
 
 
 def main():
