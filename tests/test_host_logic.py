@@ -189,3 +189,35 @@ def test_gate_tables_reproduce_the_torch_gate(layout):
             ssum = sum(go[:, a + cc * c] * xd[:, b + cc * c] for cc in range(d))
             gx[:, i] = ssum * dact(xd[:, i], kk)
     torch.testing.assert_close(gx, gx_ref, rtol=1e-12, atol=1e-12)
+
+
+def test_weighted_cta_split_covers_the_grid(monkeypatch):
+    """ops.GroupedGemm._weighted_split: every N-tile gets >= 1 CTA, ranges are disjoint and contiguous, the grid
+    is fully used, expensive tiles (long K, reduce-add stores) get more CTAs; uniform launches keep the even split."""
+    import types
+
+    import torch
+
+    from nequip_b200 import ops
+
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(multi_processor_count=148))
+    made = {}
+    real_tensor = torch.tensor
+
+    def fake_tensor(data, dtype=None, device=None):
+        made["tab"] = list(data)
+        return real_tensor(data, dtype=dtype)
+
+    monkeypatch.setattr(torch, "tensor", fake_tensor)
+    # rows: [a_off, c_off, b_off, rs_off, lda, ldc, K, N, kchunks, ntiles, tile0, flags]
+    rows = [[0, 0, 0, -1, 64, 64, 64, 64, 2, 1, 0, 0], [0, 0, 0, -1, 64, 64, 448, 384, 14, 3, 1, 4],
+            [0, 0, 0, -1, 64, 64, 64, 300, 2, 3, 4, 0]]
+    tab, G = ops.GroupedGemm._weighted_split(rows, "cuda")
+    t = made["tab"]
+    c0, n = t[0::2], t[1::2]
+    assert G == 148 and len(n) == 7 and min(n) >= 1 and sum(n) == 148
+    assert c0 == [sum(n[:i]) for i in range(7)]
+    assert min(n[1:4]) > max(n[0], *n[4:])  # K = 448 with reduce-adds is the expensive problem
+    # uniform launch: even split (None)
+    rows_u = [[0, 0, 0, -1, 128, 1728, 128, 1728, 4, 14, 0, 0]]
+    assert ops.GroupedGemm._weighted_split(rows_u, "cuda") == (None, 0)
