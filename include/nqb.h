@@ -153,7 +153,9 @@ int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const float* grad_h, 
  * FullyConnectedTensorProduct (nequip/nn/interaction_block.py:82-87,129-146) in the ir_mul layout.
  * descs_dev: device array of ndesc records of 12 int64:
  *   {a_off, c_off, b_off, rs_off (row of the [R, rs_ld] row-scale matrix, -1 = none), lda, ldc, K, N, kchunks=ceil(K/32), ntiles=ceil(N/128),
- *    tile0 (prefix sum of ntiles), flags (bit0: accumulate into C)};  offsets in floats from the bases.
+ *    tile0 (prefix sum of ntiles), flags};  offsets in floats from the bases.
+ *   flags: bit0 C += (one writer per element within the launch), bit1 rows whose row scale is 0 are left
+ *   untouched (disjoint row-masked writers), bit2 C += with red.global.add (several problems add into the same C).
  * Requirements: K, N, lda, ldc, a_off, c_off multiples of 4; bases 16-byte aligned.
  * B_p is prepared once (split hi/lo, tiled) with nqb_gemm_prepare into nqb_gemm_prepared_floats(K,N) floats.
  * tile_ctas_dev (nullable): int32 {first CTA, CTAs} per N-tile -- a cost-weighted split of sched_ctas CTAs over
