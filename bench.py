@@ -447,7 +447,7 @@ def main():
         del x, y, w, xg, yg, wg, out, go
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
         cpu = cpu_baseline(args.workload)
 
     if rank == 0:
