@@ -171,6 +171,15 @@ int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_total, const i
                      const float* a_lo_base, const float* prepared_base, float* c_base,
                      const float* rowscale_base, int64_t rs_ld, int64_t M, nqb_stream_t st);
 
+/* EXPERIMENTAL (not used by the model yet): the same product for ONE problem with K <= 128, computed transposed
+ * with the weights resident in tensor memory as the MMA's A operand (nequip_b200/csrc/nqb_gemm_t.cu).
+ * prepared: nqb_gemm_t_prepared_floats(K, N) floats written by nqb_gemm_t_prepare. */
+int64_t nqb_gemm_t_prepared_floats(int K, int N);
+int nqb_gemm_t_prepare(const float* B, int64_t ldb, int K, int N, int transposed, float scale, float* prepared,
+                       nqb_stream_t st);
+int nqb_gemm_t_run(const float* prepared, int K, int N, const float* A, int64_t lda, float* C, int64_t ldc, int64_t M,
+                   nqb_stream_t st);
+
 /* Gate nonlinearity (e3nn nn.Gate with normalize2mom'd SiLU for even / tanh for odd scalars and gates,
  * nequip/nn/convnetlayer.py:42-56,104-112), one kernel per direction.  Column tables (device, int32) are
  * built by the host from the irreps, for either layout:

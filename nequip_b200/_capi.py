@@ -53,6 +53,9 @@ SIGNATURES = {
     "nqb_mlp_hidden_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "nqb_gemm_prepared_floats": (_i64, [_i32, _i32]),
     "nqb_gemm_prepare": (_i32, [_vp, _i64, _i32, _i32, _i32, C.c_float, _vp, _vp]),
+    "nqb_gemm_t_prepared_floats": (_i64, [_i32, _i32]),
+    "nqb_gemm_t_prepare": (_i32, [_vp, _i64, _i32, _i32, _i32, C.c_float, _vp, _vp]),
+    "nqb_gemm_t_run": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _i64, _vp]),
     "nqb_gate_fwd": (_i32, [_i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nqb_gate_bwd": (_i32, [_i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "nqb_gemm_grouped": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),

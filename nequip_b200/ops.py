@@ -604,3 +604,29 @@ def gate(x: torch.Tensor, tabs: GateTables) -> torch.Tensor:
     if x.dtype not in _DT or x.dim() != 2 or x.shape[1] != tabs.d_in:
         raise ValueError("gate: x must be [N, %d] float32/float64" % tabs.d_in)
     return _GateFn.apply(x, tabs)
+
+
+# ---------------------------------------------------------------------------------------
+# EXPERIMENTAL: transposed K <= 128 GEMM with TMEM-resident weights -- nqb_gemm_t_* (opt-in tests only)
+# ---------------------------------------------------------------------------------------
+class GemmT:
+    """``C[M, N] = A[M, K] @ B[K, N]`` for K <= 128 with ``B`` prepared once."""
+
+    def __init__(self, B: torch.Tensor, device, scale: float = 1.0):
+        L = _capi.lib()
+        self.K, self.N = int(B.shape[0]), int(B.shape[1])
+        if self.K > 128 or self.K % 4:
+            raise ValueError("GemmT: K must be a multiple of 4 and <= 128")
+        Bc = B.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.prepared = torch.empty(int(L.nqb_gemm_t_prepared_floats(self.K, self.N)), dtype=torch.float32, device=device)
+        _capi.check(L.nqb_gemm_t_prepare(_ptr(Bc), Bc.shape[1], self.K, self.N, 0, float(scale), _ptr(self.prepared),
+                                         _stream()), "nqb_gemm_t_prepare")
+
+    def run(self, a: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+        _require_cuda(a, c)
+        if a.dtype != torch.float32 or c.dtype != torch.float32 or a.stride(1) != 1 or c.stride(1) != 1:
+            raise TypeError("GemmT.run: float32 row-major only")
+        M = a.shape[0]
+        _capi.check(_capi.lib().nqb_gemm_t_run(_ptr(self.prepared), self.K, self.N, _ptr(a), a.stride(0), _ptr(c),
+                                               c.stride(0), M, _stream()), "nqb_gemm_t_run")
+        return c
