@@ -40,7 +40,12 @@ WORKLOADS = {
     "asi_50k_l3_f32": ("asi", 37, dict(l_max=3, num_layers=5, num_features=32, radial_mlp_depth=1, radial_mlp_width=128)),
     "tiny": ("water", 5, dict(l_max=2, num_layers=3, num_features=8, radial_mlp_depth=1, radial_mlp_width=16)),
 }
-CPU_SAMPLE_NSIDE = {"li3po4_10k_l2_f64": 7, "water_1k_l2_f32": 8, "asi_50k_l3_f32": 9, "tiny": 4}
+# CPU arms: the sample is a smaller box of the SAME structure kind, density, r_max and model (atom-steps/s is
+# per atom, the neighbour count per atom is the same); its size is chosen from a measured per-atom cost so that
+# the whole CPU run stays within CPU_BUDGET_S -- at least 1000 atoms whenever that fits.
+CPU_SAMPLE_NSIDE_MAX = {"li3po4_10k_l2_f64": 10, "water_1k_l2_f32": 10, "asi_50k_l3_f32": 11, "tiny": 4}
+CPU_SAMPLE_NSIDE_MIN = {"li3po4_10k_l2_f64": 6, "water_1k_l2_f32": 6, "asi_50k_l3_f32": 7, "tiny": 4}
+CPU_BUDGET_S = 200.0
 R_MAX = 5.0
 
 
@@ -152,7 +157,17 @@ def pick_threads(workload):
         times[c] = time.perf_counter() - t0
     best = min(times, key=times.get)
     torch.set_num_threads(best)
-    return best, times
+    return best, times, times[best] / sysd["pos"].shape[0]
+
+
+def pick_sample_nside(workload, sec_per_atom, nsteps):
+    """Largest box (n_side^3 atoms) whose ``nsteps`` CPU steps fit CPU_BUDGET_S at the measured per-atom cost."""
+    lo, hi = CPU_SAMPLE_NSIDE_MIN[workload], CPU_SAMPLE_NSIDE_MAX[workload]
+    ns = lo
+    for n in range(lo, hi + 1):
+        if nsteps * sec_per_atom * n ** 3 <= CPU_BUDGET_S:
+            ns = n
+    return ns
 
 
 def run_reference(args, rank, world):
@@ -163,8 +178,8 @@ def run_reference(args, rank, world):
     from nequip_b200.nn.model import NequIPEnergyModel
     from oracle import model as omodel
 
-    cores, _ = pick_threads(args.workload)
-    ns = CPU_SAMPLE_NSIDE[args.workload]
+    cores, _, spa = pick_threads(args.workload)
+    ns = pick_sample_nside(args.workload, spa, args.steps + args.warmup)
     sysd, meta, mk = build_system(args.workload, seed=0, n_side=ns)
     model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
                               avg_num_neighbors=meta["avg_num_neighbors"], **mk)
@@ -195,8 +210,8 @@ def cpu_baseline(workload):
     from nequip_b200.nn.model import NequIPEnergyModel
     from oracle import model as omodel
 
-    cores, _ = pick_threads(workload)
-    ns = CPU_SAMPLE_NSIDE[workload]
+    cores, _, spa = pick_threads(workload)
+    ns = pick_sample_nside(workload, spa, 3)  # one warm-up + two timed steps
     sysd, meta, mk = build_system(workload, seed=0, n_side=ns)
     model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
                               avg_num_neighbors=meta["avg_num_neighbors"], **mk)
@@ -205,7 +220,7 @@ def cpu_baseline(workload):
     omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=20000)
     t0 = time.perf_counter()
     reps = 0
-    while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 20):
+    while reps < 2:
         omodel.energy_and_forces(sd, cfg, sysd, torch.float32, tp_chunk=20000)
         reps += 1
     dt = (time.perf_counter() - t0) / reps

@@ -96,6 +96,22 @@ int nqb_tp_scatter_bwd(const nqb_plan* plan, int dtype, const void* x, const voi
                        const void* grad_out, int64_t N, int64_t E, void* grad_x, void* grad_y,
                        void* grad_w, nqb_stream_t st);
 
+/* Fused "last radial-MLP layer -> tensor product -> scatter" forward:
+ *   out[n] = sum_{e: dst[e] = n} TP_uvu(x[src[e]], y[e], w[e]),   w[e] = h[e, :K] @ (W2 * alpha2)
+ * i.e. nequip/nn/mlp.py:262-268 (the last ScalarLinearLayer built at nequip/nn/interaction_block.py:119-127)
+ * composed with TensorProductScatter.forward (nequip/nn/_tp_scatter_base.py:35-38) so that the [E, W] weight
+ * tensor is never written (w_out == NULL) -- or is written once on the side for an unfused backward.
+ * float32, ir_mul node layout, edges grouped by destination (row_ptr; no permutation), K <= 128, K % 8 == 0.
+ * nqb_tp_fused_slices(plan): number of 128-row weight slices of the signature, 0 = no fused kernel built.
+ * w2_prepared: nqb_gemm_t_prepare() of the [K, 128 * slices] weight matrix whose COLUMNS are in slice order
+ *   (nequip_b200/codegen.py TPGenerator.fused_layout()["cols"], -1 = zero column), scaled by alpha2.
+ * slice_cta0 [slices + 1] (device, int32): CTAs [cta0[s], cta0[s+1]) process slice s; nctas = cta0[slices]
+ *   (one CTA per SM; the host splits the grid in proportion to the slices' costs). */
+int nqb_tp_fused_slices(const nqb_plan* plan);
+int nqb_tp_fused_fwd(const nqb_plan* plan, const float* x, const float* y, const float* h, int64_t ldh, int K,
+                     const float* w2_prepared, const int64_t* row_ptr, const int64_t* src, int64_t N, int64_t E,
+                     float* out, float* w_out, const int32_t* slice_cta0, int nctas, nqb_stream_t st);
+
 /* Real spherical harmonics, "component" normalisation, input normalised (lmax <= 3).
  *   vec [E,3] f64 -> y [E,(lmax+1)^2] of out_dtype (computed in f64, then cast). */
 int nqb_sh_fwd(int lmax, const double* vec, int64_t E, int out_dtype, void* y, nqb_stream_t st);
@@ -120,27 +136,12 @@ int nqb_edge_embed_bwd(int lmax, int num_bessel, double r_max, double poly_p, do
                        int out_dtype, const void* grad_y, const void* grad_emb, double* grad_pos,
                        double* grad_vec, nqb_stream_t st);
 
-/* Radial MLP on the tensor cores (tcgen05, 3xTF32 split = fp32-level accuracy):
- *   edge_weight[E, W] = silu(emb[E, 8] @ W1s[8, 128]) @ (W2[128, W] * alpha2)
- * replaces ScalarMLPFunction.forward for the depth-1 / width-128 radial network that
- * InteractionBlock builds (nequip/nn/mlp.py:80-195,262-268; nequip/nn/interaction_block.py:119-127,196).
- * W1s is the first-layer weight already multiplied by its alpha.  nqb_mlp_prepare lays the
- * second-layer weight out for the MMA tiles once per model (two buffers of
- * nqb_mlp_prepared_bytes(W) bytes each).  W must be a multiple of 32. */
-size_t nqb_mlp_prepared_bytes(int W);
-int nqb_mlp_prepare(const float* W2, float alpha2, int hidden, int W, float* prep_fwd, float* prep_bwd,
-                    nqb_stream_t st);
-int nqb_mlp_fwd(const float* emb, const float* W1s, const float* prep_fwd, int64_t E, int num_bessel,
-                int hidden, int W, float* edge_weight, nqb_stream_t st);
-/* grad_emb[E, 8] = ((grad_w @ (W2 alpha2)^T) * silu'(emb @ W1s)) @ W1s^T   (overwritten) */
-int nqb_mlp_bwd(const float* emb, const float* W1s, const float* prep_bwd, const float* grad_w, int64_t E,
-                int num_bessel, int hidden, int W, float* grad_emb, nqb_stream_t st);
-
 /* First radial layer (K = 8, CUDA cores):  h[E,128] = silu(emb[E,8] @ W1s[8,128])  and
  * grad_emb[E,8] = (grad_h * silu'(emb @ W1s)) @ W1s^T  (pre-activation recomputed, nothing saved).
  * Together with nqb_gemm_grouped for the second layer this is ScalarMLPFunction (nequip/nn/mlp.py:80-195). */
-/* h_lo (nullable): the part of h the tensor core does not see, h_lo = rna_tf32(h - trunc_tf32(h)); handing it
- * to nqb_gemm_grouped as a_lo_base saves that kernel the operand-split pass. */
+/* h_lo (nullable): the part of h the tensor core does not see, h_lo = rna_tf32(h - trunc_tf32(h)).  It can be
+ * handed to nqb_gemm_grouped as a_lo_base, but that form doubles the A reads and limits the producer ring to one
+ * piece in flight (measured 1.7x slower, profiles/r01_gemm_roles.txt): the product path passes NULL for both. */
 int nqb_mlp_hidden_fwd(const float* emb, const float* W1s, int64_t E, int num_bessel, int hidden, float* h,
                        float* h_lo, nqb_stream_t st);
 int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const float* grad_h, int64_t E, int num_bessel,

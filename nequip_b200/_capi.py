@@ -43,6 +43,8 @@ SIGNATURES = {
     "nqb_tp_scatter_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "nqb_tp_scatter_bwd": (
         _i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "nqb_tp_fused_slices": (_i32, [_vp]),
+    "nqb_tp_fused_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
     "nqb_sh_fwd": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp]),
     "nqb_sh_bwd": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "nqb_edge_embed_fwd": (
@@ -59,10 +61,6 @@ SIGNATURES = {
     "nqb_gate_fwd": (_i32, [_i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nqb_gate_bwd": (_i32, [_i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "nqb_gemm_grouped": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
-    "nqb_mlp_prepared_bytes": (C.c_size_t, [_i32]),
-    "nqb_mlp_prepare": (_i32, [_vp, C.c_float, _i32, _i32, _vp, _vp, _vp]),
-    "nqb_mlp_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
-    "nqb_mlp_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
 }
 
 

@@ -94,15 +94,19 @@ def ensure_spec(sig: TPSignature, opts: Optional[GenOptions] = None, force: bool
             return out
         os.makedirs(LIBDIR, exist_ok=True)
         os.makedirs(GENDIR, exist_ok=True)
-        cu = os.path.join(GENDIR, os.path.basename(out)[:-3] + ".cu")
+        # several ranks may JIT the same signature at once: every process writes its own source and
+        # temporary library, the final rename is atomic
+        cu = os.path.join(GENDIR, os.path.basename(out)[:-3] + f".{os.getpid()}.cu")
         with open(cu, "w") as f:
             f.write(generate(sig, opts))
+        final_cu = os.path.join(GENDIR, os.path.basename(out)[:-3] + ".cu")
         tmp = out + f".tmp{os.getpid()}"
         cmd = [nvcc_path(), *ARCH_FLAGS, *COMMON_FLAGS, "-I", CSRC, "-o", tmp, cu]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         log = _run(cmd)
         os.replace(tmp, out)
+        os.replace(cu, final_cu)
         if verbose:
             print(log)
     return out

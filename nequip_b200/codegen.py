@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 13
+CODEGEN_VERSION = 15
 
 
 # ---------------------------------------------------------------------------
@@ -208,6 +208,10 @@ class _Emitter:
 
 def _imm(v: float) -> str:
     return f"T({v!r})"
+
+
+def _imm_f(v: float) -> str:
+    return f"{v!r}f"
 
 
 def _pow2ceil(n: int) -> int:
@@ -794,6 +798,163 @@ class TPGenerator:
         em.end()
         em()
 
+    # -- fused radial-MLP + TP + scatter forward (csrc/nqb_tp_fused.cuh) ---------------------
+    def path_cost(self, p: Path) -> int:
+        """Issue-slot estimate of one edge PAIR for one channel of path ``p`` in the fused consumer."""
+        n1, n2, n3 = 2 * p.l1 + 1, 2 * p.l2 + 1, 2 * p.l3 + 1
+        if p.l2 == 0:
+            fma = 2 + n3
+        else:
+            sp = cg.sparse_w3j(p.l1, p.l2, p.l3)
+            fma = len(sp) + len({(i, j) for (i, j, _k, _c) in sp}) + n3
+        return fma + 2 * n1 + n2 + 6
+
+    def fused_layout(self):
+        """Slices of the path-parallel fused kernel, or None when the signature is not eligible.
+
+        A slice is 128 consecutive (path, channel) rows = 128 // mul whole paths; paths that read the same
+        input chunk are kept together (one staged x row per edge and slice).  Returns a dict with
+        ``slices`` (lists of Path), per-slice ``segs`` [(x offset, floats)], ``cols`` (weight column of every
+        row, -1 = padding), ``cost`` per slice, ``xrow`` (max staged floats per edge) and ``nxs`` (ring stages)."""
+        sig = self.sig
+        if self.opts.layout != "ir_mul":
+            return None
+        muls = {p.mul for p in sig.paths}
+        if len(muls) != 1:
+            return None
+        mul = muls.pop()
+        if mul % 32 != 0 or 128 % mul != 0:
+            return None
+        if sorted(p.io for p in sig.paths) != list(range(len(sig.irreps_out))):
+            return None  # every output chunk must be written by exactly one path
+        pps = 128 // mul
+        by_i1: Dict[int, List[Path]] = {}
+        for p in sig.paths:
+            by_i1.setdefault(p.i1, []).append(p)
+        slices: List[List[Path]] = []
+        rest: List[Path] = []
+        for i1 in sorted(by_i1):
+            ps = sorted(by_i1[i1], key=self.path_cost, reverse=True)
+            while len(ps) >= pps:  # heavy and light paths alternate so that slices cost about the same
+                grp = [ps.pop(0) if t % 2 == 0 else ps.pop() for t in range(pps)]
+                slices.append(grp)
+            rest += ps
+        rest.sort(key=lambda p: p.i1)
+        while rest:
+            slices.append(rest[:pps])
+            rest = rest[pps:]
+        segs, xrow = [], 0
+        for grp in slices:
+            chunks = sorted({p.i1 for p in grp})
+            sg = [(sig.irreps_in1.offsets()[i1], sig.irreps_in1[i1][0] * sig.irreps_in1[i1][1].dim, i1) for i1 in chunks]
+            if len(sg) > 4:
+                return None
+            segs.append(sg)
+            xrow = max(xrow, sum(n for (_o, n, _i) in sg))
+        if xrow % 4 or sig.d_in % 4:
+            return None
+        fixed = 2 * 2 * 64 * 128 * 4 + 1024  # h tiles (hi, lo) x 2 stages + barriers
+        stage = 8 * (xrow + sig.s_dim) * 4
+        nxs = min(16, (227 * 1024 - 1024 - fixed) // stage)
+        if nxs < 6:
+            return None
+        cols = []
+        for grp in slices:
+            for p in grp:
+                cols += [p.woff + u for u in range(mul)]
+            cols += [-1] * (128 - mul * len(grp))
+        cost = [sum(self.path_cost(p) for p in grp) * (mul // 32) for grp in slices]
+        return dict(mul=mul, pps=pps, slices=slices, segs=segs, xrow=xrow, nxs=int(nxs), cols=cols, cost=cost)
+
+    def _emit_fused_path(self, em: _Emitter, p: Path, xs_off: int, mul: int):
+        sig = self.sig
+        n1, n2, n3 = 2 * p.l1 + 1, 2 * p.l2 + 1, 2 * p.l3 + 1
+        boff, mtot, ubase = self.out_ir_mul(p.io)
+        em.block(f"struct FtPath{p.idx}")
+        em("static constexpr bool ACTIVE = true;")
+        em(f"static constexpr int N1 = {n1}, N2 = {n2}, N3 = {n3}, XS_OFF = {xs_off}, Y_OFF = {p.yoff}, W_OFF = {p.woff}, MUL = {mul};")
+        em.block("static __device__ __forceinline__ void fma(const float2* x, const float2* y, float2 w, float2* a)")
+        if p.l2 == 0:
+            kappa = p.coef * cg.real_w3j(p.l1, 0, p.l3)[0][0][0]
+            em(f"const float2 ws = vmul(w, vmuli(y[0], {_imm_f(kappa)}));")
+            for k in range(n1):
+                em(f"a[{k}] = vfma(ws, x[{k}], a[{k}]);")
+        else:
+            fan: Dict[Tuple[int, int], List[Tuple[int, float]]] = {}
+            for (i, j, k, c) in cg.sparse_w3j(p.l1, p.l2, p.l3):
+                fan.setdefault((i, j), []).append((k, p.coef * c))
+            em("float2 " + ", ".join(f"v{k}" for k in range(n3)) + ";")
+            started = set()
+            for (i, j) in sorted(fan):
+                em.block()
+                em(f"const float2 t = vmul(x[{i}], y[{j}]);")
+                for (k, c) in fan[(i, j)]:
+                    if k not in started:
+                        em(f"v{k} = vmuli(t, {_imm_f(c)});")
+                        started.add(k)
+                    else:
+                        em(f"v{k} = vfmai(t, {_imm_f(c)}, v{k});")
+                em.end()
+            for k in range(n3):
+                if k in started:
+                    em(f"a[{k}] = vfma(w, v{k}, a[{k}]);")
+        em.end()
+        em.block("static __device__ __forceinline__ void store(float* __restrict__ o, int u, const float2* a)")
+        for k in range(n3):
+            em(f"o[{boff + ubase + k * mtot} + u] = a[{k}].x + a[{k}].y;")
+        em.end()
+        em.block("static __device__ __forceinline__ void store_zero(float* __restrict__ o, int u)")
+        for k in range(n3):
+            em(f"o[{boff + ubase + k * mtot} + u] = 0.f;")
+        em.end()
+        em.end("};")
+
+    def _emit_fused(self, em: _Emitter) -> bool:
+        lay = self.fused_layout()
+        if lay is None:
+            return False
+        sig = self.sig
+        mul, slices, segs = lay["mul"], lay["slices"], lay["segs"]
+        ns = len(slices)
+        for si, grp in enumerate(slices):
+            soff = {}
+            o = 0
+            for (_goff, n, i1) in segs[si]:
+                soff[i1] = o
+                o += n
+            for p in grp:
+                self._emit_fused_path(em, p, soff[p.i1], mul)
+        flat_len, flat_goff, cnt = [], [], []
+        for si in range(ns):
+            sg = segs[si] + [(0, 0, -1)] * (4 - len(segs[si]))
+            cnt.append(len(segs[si]))
+            flat_goff += [g for (g, _n, _i) in sg]
+            flat_len += [n for (_g, n, _i) in sg]
+        em(f"__constant__ int FT_SEG_CNT[{ns}] = {{{', '.join(map(str, cnt))}}};")
+        em(f"__constant__ int FT_SEG_GOFF[{ns * 4}] = {{{', '.join(map(str, flat_goff))}}};")
+        em(f"__constant__ int FT_SEG_LEN[{ns * 4}] = {{{', '.join(map(str, flat_len))}}};")
+        em.block("struct FtSpec")
+        em(f"static constexpr int MUL = {mul}, S = {sig.s_dim}, D_IN = {sig.d_in}, D_OUT = {sig.d_out}, W = {sig.weight_numel}, "
+           f"NSLICE = {ns}, XROW = {lay['xrow']}, NXS = {lay['nxs']};")
+        em("static __device__ __forceinline__ int seg_count(int s) { return FT_SEG_CNT[s]; }")
+        em("static __device__ __forceinline__ int seg_goff(int s, int k) { return FT_SEG_GOFF[s * 4 + k]; }")
+        em("static __device__ __forceinline__ int seg_len(int s, int k) { return FT_SEG_LEN[s * 4 + k]; }")
+        em.block("static __device__ __forceinline__ void consume(int slice, int quad, int lane, const FusedFwdArgs& a, FtSmem& S, "
+                 "const float* xring, uint32_t tmem)")
+        em.block("switch (slice * 4 + quad)")
+        wpp = mul // 32  # warps per path
+        for si, grp in enumerate(slices):
+            for q in range(4):
+                slot = q // wpp
+                if slot < len(grp):
+                    p = grp[slot]
+                    em(f"case {si * 4 + q}: ft_consumer<FtPath{p.idx}, FtSpec>(a, S, xring, tmem, quad, lane, {(q % wpp) * 32} + lane); break;")
+        em("default: ft_consumer<FtNullPath, FtSpec>(a, S, xring, tmem, quad, lane, lane); break;")
+        em.end()
+        em.end()
+        em.end("};")
+        return True
+
     # -- translation unit ----------------------------------------------------------------
     def source(self) -> str:
         sig = self.sig
@@ -805,6 +966,7 @@ class TPGenerator:
         em(f"// options: {self.opts.tag()}  fwd_groups={len(self.fwd_groups)} bwd_groups={len(self.bwd_groups)}")
         em(f"// forward multiply-accumulates per (edge, channel): {sig.fma_count()}")
         em("#include <cuda_runtime.h>")
+        em('#include "nqb_tc.cuh"')
         em("namespace {")
         em(f"constexpr int NWARP = {self.opts.nwarp};")
         em("template <typename T> struct VT;")
@@ -820,13 +982,18 @@ class TPGenerator:
         em(f"constexpr int NGB = {len(self.bwd_groups)};")
         em("}  // namespace")
         em('#include "nqb_tp_device.cuh"')
+        em('#include "nqb_tp_fused.cuh"')
         em("namespace {")
         em()
+        self.has_fused = self._emit_fused(em)
         for gid, ps in enumerate(self.fwd_groups):
             self._emit_fwd_group(em, gid, ps)
         # the ring pays off when several warps (path groups) share one node's weight rows; single-group
         # signatures (3-4 paths: first/last layer) keep the register-resident v1 kernel (measured)
-        self.use_ring = bool(self.opts.fwd_ring and sig.weight_numel % 4 == 0 and len(self.fwd_groups) >= 2)
+        # (and only while the ring fits: a signature whose ring would exceed ~200 KB keeps the register kernel)
+        ring_bytes = self.opts.ring_stages * self.geometry(2)[1] * sig.weight_numel * 4 + 2 * self.opts.ring_stages * 8 + 256 * 16
+        ring_fits = ring_bytes <= 200 * 1024
+        self.use_ring = bool(self.opts.fwd_ring and sig.weight_numel % 4 == 0 and len(self.fwd_groups) >= 2 and ring_fits)
         if self.use_ring:
             em(f"constexpr int F2_STAGES = {self.opts.ring_stages};")
             em("constexpr int F2_CAP = 256;")
@@ -835,7 +1002,7 @@ class TPGenerator:
                 self._emit_fwd2_group(em, gid, ps)
         for gid, ps in enumerate(self.bwd_groups):
             self._emit_bwd_group(em, gid, ps)
-        self.use_ring_bwd = bool(self.opts.bwd_ring and sig.weight_numel % 4 == 0 and len(self.bwd_groups) >= 2)
+        self.use_ring_bwd = bool(self.opts.bwd_ring and sig.weight_numel % 4 == 0 and len(self.bwd_groups) >= 2 and ring_fits)
         if self.use_ring_bwd:
             em(f"constexpr int B2_STAGES = {self.opts.ring_stages};")
             em("constexpr int B2_CAP = 256;")
@@ -997,8 +1164,13 @@ class TPGenerator:
             lpe_f2, epw_f2, cb_f2 = self.geometry(2)
             smem = self.opts.ring_stages * epw_f2 * sig.weight_numel * 4 + 2 * self.opts.ring_stages * 8 + 256 * 16
             em(f"constexpr int F2_SMEM = {smem};")
-            em("static bool attr_set = false;")
-            em("if (!attr_set) { cudaFuncSetAttribute(tp_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM); attr_set = true; }")
+            em("static bool attr_set[64] = {false};  // per device")
+            em("int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63;")
+            em.block("if (!attr_set[dev_])")
+            em("cudaError_t e_ = cudaFuncSetAttribute(tp_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);")
+            em("if (e_ != cudaSuccess) return (int)e_;")
+            em("attr_set[dev_] = true;")
+            em.end()
             em("dim3 grid2((unsigned)N, VT<float>::CB), block2(32 * NGF);")
             em("tp_fwd2_kernel<<<grid2, block2, F2_SMEM, st>>>((const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, N, (float*)out);")
         else:
@@ -1024,11 +1196,13 @@ class TPGenerator:
             smemb = self.opts.ring_stages * epw_f2 * sig.weight_numel * 4 + 2 * self.opts.ring_stages * 8 + 256 * 16
             em.block("if (dtype == 0)")
             em(f"constexpr int B2_SMEM = {smemb};")
-            em("static bool attr_set = false;")
-            em.block("if (!attr_set)")
-            em("cudaFuncSetAttribute(tp_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);")
-            em("cudaFuncSetAttribute(tp_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);")
-            em("attr_set = true;")
+            em("static bool attr_set[64] = {false};  // per device")
+            em("int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63;")
+            em.block("if (!attr_set[dev_])")
+            em("cudaError_t e_ = cudaFuncSetAttribute(tp_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);")
+            em("if (e_ == cudaSuccess) e_ = cudaFuncSetAttribute(tp_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);")
+            em("if (e_ != cudaSuccess) return (int)e_;")
+            em("attr_set[dev_] = true;")
             em.end()
             em("dim3 grid2((unsigned)N, VT<float>::CB), block2(32 * NGB);")
             a2 = ("(const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, (const float*)gout, N, "
@@ -1048,6 +1222,35 @@ class TPGenerator:
             em(f"else tp_bwd_kernel<{name}, false><<<grid, block, 0, st>>>({args});")
             em.end()
         em("return (int)cudaGetLastError();")
+        em.end()
+        # fused radial-MLP last layer + TP + scatter forward; -1 = not built for this signature
+        em.block('extern "C" int nqb_spec_fused_info(int* nslice, int* nxs, int* xrow)')
+        if self.has_fused:
+            em("*nslice = FtSpec::NSLICE; *nxs = FtSpec::NXS; *xrow = FtSpec::XROW; return 0;")
+        else:
+            em("*nslice = 0; *nxs = 0; *xrow = 0; return -1;")
+        em.end()
+        em.block('extern "C" int nqb_spec_fused_fwd(const float* x, const float* y, const float* h, int64_t ldh, int K, '
+                 "const float* wprep, const int64_t* row_ptr, const int64_t* src, int64_t N, int64_t E, float* out, "
+                 "float* w_out, const int32_t* slice_cta0, int nctas, cudaStream_t st)")
+        if self.has_fused:
+            em("if (N <= 0) return 0;")
+            em("if (K <= 0 || K > FT_KMAX || (K % 8) || (ldh % 4) || nctas <= 0) return (int)cudaErrorInvalidValue;")
+            em("const size_t smem = ft_smem_bytes<FtSpec>();")
+            em("static bool attr_set[64] = {false};  // per device")
+            em("int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63;")
+            em.block("if (!attr_set[dev_])")
+            em("cudaError_t e_ = cudaFuncSetAttribute(tp_fused_fwd_kernel<FtSpec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+            em("if (e_ != cudaSuccess) return (int)e_;")
+            em("attr_set[dev_] = true;")
+            em.end()
+            em("FusedFwdArgs a;")
+            em("a.x = x; a.y = y; a.h = h; a.wprep = wprep; a.row_ptr = row_ptr; a.src = src; a.out = out; a.w_out = w_out;")
+            em("a.slice_cta0 = slice_cta0; a.N = N; a.E = E; a.ldh = ldh; a.K = K;")
+            em("tp_fused_fwd_kernel<FtSpec><<<nctas, FT_THREADS, smem, st>>>(a);")
+            em("return (int)cudaGetLastError();")
+        else:
+            em("return -1;")
         em.end()
         return em.text()
 

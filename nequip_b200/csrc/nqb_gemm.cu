@@ -568,15 +568,20 @@ extern "C" int nqb_gemm_prof_read(unsigned long long* out) {
 }
 #endif
 
+// per-device state (one process may drive several GPUs: attributes and SM counts are per device)
+static int gemm_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 63;
+}
 static int gemm_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};
+  const int dev = gemm_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 extern "C" int64_t nqb_gemm_prepared_floats(int K, int N) {
@@ -607,11 +612,12 @@ extern "C" int nqb_gemm_grouped(const void* descs_dev, int ndesc, int ntiles_tot
   if (M < 0) return nqb_set_error("nqb_gemm_grouped: negative M");
   if (M == 0) return 0;
   if (!descs_dev || !a_base || !prepared_base || !c_base) return nqb_set_error("nqb_gemm_grouped: null pointer");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  const int dev = gemm_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm3x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
     if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int64_t nwork = ((M + TM - 1) / TM) * (int64_t)ntiles_total;
   int grid = (int)(nwork < gemm_sm_count() ? nwork : gemm_sm_count());

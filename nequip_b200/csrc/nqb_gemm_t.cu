@@ -319,17 +319,19 @@ extern "C" int nqb_gemm_t_run(const float* prepared, int K, int N, const float* 
   if (M == 0) return 0;
   if (!prepared || !A || !C) return nqb_set_error("nqb_gemm_t_run: null pointer");
   if (K <= 0 || K > KMAX || N <= 0 || (K % 4) || (lda % 4)) return nqb_set_error("nqb_gemm_t_run: needs 0 < K <= 128, K and lda multiples of 4");
-  static bool attr_set = false;
-  static int sms = 0;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  static int sms_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm3x_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT) + 1024);
     if (e != cudaSuccess) return nqb_set_error(cudaGetErrorString(e));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    attr_set = true;
+    cudaDeviceGetAttribute(&sms_dev[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms_dev[dev] <= 0) sms_dev[dev] = 148;
+    attr_set[dev] = true;
   }
+  const int sms = sms_dev[dev];
   const int ntiles = (N + TW - 1) / TW;
   const int64_t nwork = ((M + TE - 1) / TE) * (int64_t)ntiles;
   const int grid = (int)(nwork < sms ? nwork : sms);

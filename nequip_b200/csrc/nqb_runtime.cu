@@ -68,11 +68,17 @@ typedef int (*spec_fwd_fn)(int, const void*, const void*, const void*, const int
 typedef int (*spec_bwd_fn)(int, const void*, const void*, const void*, const int64_t*, const int64_t*,
                            const int64_t*, const void*, int64_t, int64_t, void*, void*, void*, cudaStream_t);
 
+typedef int (*spec_fused_info_fn)(int*, int*, int*);
+typedef int (*spec_fused_fwd_fn)(const float*, const float*, const float*, int64_t, int, const float*, const int64_t*,
+                                 const int64_t*, int64_t, int64_t, float*, float*, const int32_t*, int, cudaStream_t);
+
 struct nqb_plan {
   std::string signature;
   void* lib;
   spec_fwd_fn fwd;
   spec_bwd_fn bwd;
+  spec_fused_fwd_fn fused_fwd = nullptr;  // null: the signature has no fused radial-MLP + TP kernel
+  int fused_nslice = 0;
   int d_in, s_dim, w_numel, d_out;
 };
 
@@ -134,6 +140,10 @@ extern "C" int nqb_plan_create(const nqb_irrep* in1, int n_in1, const nqb_irrep*
   p->fwd = ffwd;
   p->bwd = fbwd;
   fdims(&p->d_in, &p->s_dim, &p->w_numel, &p->d_out);
+  spec_fused_info_fn finfo = (spec_fused_info_fn)dlsym(lib, "nqb_spec_fused_info");
+  spec_fused_fwd_fn ffused = (spec_fused_fwd_fn)dlsym(lib, "nqb_spec_fused_fwd");
+  int nxs = 0, xrow = 0;
+  if (finfo && ffused && finfo(&p->fused_nslice, &nxs, &xrow) == 0 && p->fused_nslice > 0) p->fused_fwd = ffused;
   *plan = p;
   return 0;
 }
@@ -192,6 +202,28 @@ extern "C" int nqb_tp_scatter_bwd(const nqb_plan* plan, int dtype, const void* x
   int rc = plan->bwd(dtype, x, y, w, row_ptr, perm, src, grad_out, N, E, grad_x, grad_y, grad_w, (cudaStream_t)st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (rc) return cuda_fail((cudaError_t)rc, "nqb_tp_scatter_bwd launch");
+  return 0;
+}
+
+extern "C" int nqb_tp_fused_slices(const nqb_plan* plan) {
+  if (!plan || !plan->fused_fwd) return 0;
+  return plan->fused_nslice;
+}
+
+extern "C" int nqb_tp_fused_fwd(const nqb_plan* plan, const float* x, const float* y, const float* h, int64_t ldh, int K,
+                                const float* w2_prepared, const int64_t* row_ptr, const int64_t* src, int64_t N, int64_t E,
+                                float* out, float* w_out, const int32_t* slice_cta0, int nctas, nqb_stream_t st) {
+  if (!plan) return fail("nqb_tp_fused_fwd: null plan");
+  if (!plan->fused_fwd) return fail("nqb_tp_fused_fwd: this signature has no fused kernel (nqb_tp_fused_slices() == 0)");
+  if (N < 0 || E < 0) return fail("nqb_tp_fused_fwd: negative size");
+  if (N == 0) return 0;
+  if (!row_ptr || !out || !w2_prepared || !slice_cta0 || (E > 0 && (!x || !y || !h || !src)))
+    return fail("nqb_tp_fused_fwd: null pointer argument");
+  if (K <= 0 || K > 128 || (K % 8) || (ldh % 4) || ldh < K) return fail("nqb_tp_fused_fwd: needs 0 < K <= 128, K %% 8 == 0, ldh %% 4 == 0");
+  if (nctas <= 0) return fail("nqb_tp_fused_fwd: empty grid");
+  int rc = plan->fused_fwd(x, y, h, ldh, K, w2_prepared, row_ptr, src, N, E, out, w_out, slice_cta0, nctas, (cudaStream_t)st);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc) return cuda_fail((cudaError_t)rc, "nqb_tp_fused_fwd launch");
   return 0;
 }
 

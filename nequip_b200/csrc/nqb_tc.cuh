@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy PTX vocabulary shared by the tensor-core kernels (sm_100a).
 // Bit layouts follow cute::UMMA::SmemDescriptor / InstrDescriptor (CUTLASS mma_sm100_desc.hpp).
 #pragma once
+#define NQB_TC_HELPERS 1  // nqb_tp_device.cuh skips its own copies of the mbarrier / bulk-copy helpers
 #include <cuda_runtime.h>
 #include <stdint.h>
 

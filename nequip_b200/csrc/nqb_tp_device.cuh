@@ -164,6 +164,7 @@ template <int MUL, bool AL2> __device__ __forceinline__ void vstorew(double* __r
   if (full || ch0 < MUL) p[0] = v;
 }
 
+#ifndef NQB_TC_HELPERS
 // ---- shared-memory weight ring (forward v2): mbarrier + cp.async.bulk ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -192,6 +193,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+#endif  // NQB_TC_HELPERS
 // weights of the channel pair from the shared-memory ring
 template <int MUL, bool AL2> __device__ __forceinline__ float2 vloadws(const float* p, int ch0, bool valid) {
   constexpr bool full = (MUL % (VT<float>::LPE * 2)) == 0;

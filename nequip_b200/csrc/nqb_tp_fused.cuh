@@ -1,0 +1,432 @@
+// Fused radial-MLP last layer -> tensor product -> scatter, forward (sm_100a).   SURVEY.md section 8(f)-1.
+//
+// Reference ops fused here (paths under /root/reference):
+//   edge_weight = h @ (W2 * alpha2)                      nequip/nn/mlp.py:262-268 (last ScalarLinearLayer of
+//                                                         the radial MLP, built at interaction_block.py:119-127)
+//   out = scatter(tp(x[src], edge_attr, edge_weight))     nequip/nn/_tp_scatter_base.py:35-38,
+//                                                         nequip/nn/interaction_block.py:193-199
+// so that the [E, W] edge-weight tensor (92 % of the unfused kernel's bytes) never leaves the SM.
+//
+// Decomposition: PATH-parallel.  The W columns (path p, channel u) are cut into slices of 128; a CTA owns ONE
+// slice for a contiguous node range, keeps the slice's second-layer weights W2^T[128 (p,u), K <= 128] (tf32 hi and
+// lo parts) RESIDENT in tensor memory as the MMA "A" operand for its whole life, and streams its edges through
+//   D^T[(p,u), e] = sum_k W2^T[(p,u), k] * h[e, k]            (tcgen05.mma kind::tf32, 3xTF32 split, A from TMEM,
+//                                                              B = the h rows, K-major canonical layout in smem)
+// one destination node (<= 64 edges) per MMA tile.  D^T has TMEM lane = (p,u) and column = edge, which is exactly
+// the thread mapping of the tensor-product arithmetic (thread = one channel of one path, loop over the node's
+// edges): consumer warps read their weights straight from TMEM with tcgen05.ld -- no shared-memory transpose --
+// contract two edges at a time as packed FFMA2 (x = {x[src_e0], x[src_e1]}, Y = {Y_e0, Y_e1}, w = adjacent TMEM
+// columns), keep the node's output in registers and write each output element exactly once (deterministic, no
+// atomics, no zero fill).  Weights are never re-streamed: 128 KB per CTA once, instead of 1.8 MB per 128 edges.
+//
+// Roles (384 threads): warps 0-3 consumers (TMEM lane quadrant = warp), warps 4-7 producers (cp.async: h tile +
+// its tf32 low part; x[src] rows and Y rows of the node's edges into an 8-edge-stage ring), warp 8 MMA issue.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nqb_tc.cuh"
+
+namespace {
+
+constexpr int FT_TE = 64;                       // max edges per tile = MMA N
+constexpr int FT_KMAX = 128;                    // resident K (hidden width of the radial MLP)
+constexpr int FT_SUB = 8;                       // edges per x/Y ring stage
+constexpr int FT_TILE_FLOATS = FT_TE * FT_KMAX; // 32 KB
+constexpr int FT_THREADS = 384;
+constexpr int FT_MAXSEG = 4;                    // distinct input chunks a slice may stage per edge
+
+struct FusedFwdArgs {
+  const float* x;        // [N, D_IN]  ir_mul layout
+  const float* y;        // [E, S]
+  const float* h;        // [E, ldh]   hidden activations of the radial MLP
+  const float* wprep;    // [NSLICE][hi|lo][128][FT_KMAX]  (nqb_gemm_t_prepare layout, rows in slice order)
+  const int64_t* row_ptr;
+  const int64_t* src;
+  float* out;            // [N, D_OUT]
+  float* w_out;          // [E, W] or nullptr: the per-edge weights in instruction order (for an unfused backward)
+  const int32_t* slice_cta0;  // [NSLICE + 1]: CTAs [cta0[s], cta0[s+1]) work on slice s
+  int64_t N, E, ldh;
+  int K;                 // hidden width, multiple of 8, <= FT_KMAX
+};
+
+// tcgen05.mma with the A operand in tensor memory
+__device__ __forceinline__ void ft_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ft_tmem_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void ft_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// two 32-lane x 16-column loads (hi*hi and cross-term accumulators), one wait
+__device__ __forceinline__ void ft_tmem_ld16x2(uint32_t ta, uint32_t tb, float* va, float* vb) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(r[i]); vb[i] = __uint_as_float(r[16 + i]); }
+}
+
+__device__ __forceinline__ void ft_cp_async4(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once all cp.async operations this thread has issued so far have landed (the arrival is counted
+// in the barrier's expected count: .noinc)
+__device__ __forceinline__ void ft_cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// shared memory: fixed part; the x/Y ring (NXS stages of STAGE_FLOATS floats) follows it
+struct FtSmem {
+  float hraw[2][FT_TILE_FLOATS];   // h tiles (the fp32 tile is the tf32 high operand: the tensor core truncates)
+  float hlo[2][FT_TILE_FLOATS];    // their tf32 low parts
+  uint64_t a_full[2], a_done[2], acc_full[2], acc_empty[2], w_full;
+  uint64_t x_full[16], x_empty[16];
+  uint32_t tmem_base;
+  int slice, pad_;
+  int64_t n0, n1;
+};
+
+// first n in [0, N] with row_ptr[n] >= t
+__device__ __forceinline__ int64_t ft_lower_bound(const int64_t* __restrict__ row_ptr, int64_t N, int64_t t) {
+  int64_t lo = 0, hi = N;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (row_ptr[mid] < t) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// consumer: one warp = 32 channels of one path (TMEM lanes quad*32 .. +31)
+// PathT (generated): ACTIVE, N1/N2/N3 (= 2l+1), XS_OFF (float offset of the input chunk inside a staged edge row),
+// Y_OFF, W_OFF, MUL, and  fma(x[N1], y[N2], w, acc[N3]),  store(out_row, u, acc),  store_zero(out_row, u)
+// ---------------------------------------------------------------------------------------------------------
+template <class P, class Spec>
+__device__ __forceinline__ void ft_consumer(const FusedFwdArgs& a, FtSmem& S, const float* xring, uint32_t tmem, int quad,
+                                            int lane, int u) {
+  constexpr int NXS = Spec::NXS, XROW = Spec::XROW, SD = Spec::S;
+  constexpr int STAGE_FLOATS = FT_SUB * (XROW + SD);
+  const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+  const int64_t n0 = S.n0, n1 = S.n1;
+  float2 acc[P::N3 > 0 ? P::N3 : 1];
+#pragma unroll
+  for (int k = 0; k < P::N3; ++k) acc[k] = make_float2(0.f, 0.f);
+  uint32_t it = 0, xs = 0;
+  for (int64_t n = n0; n < n1; ++n) {
+    const int64_t beg = a.row_ptr[n], end = a.row_ptr[n + 1];
+    if (beg == end) {
+      if (P::ACTIVE) P::store_zero(a.out + n * Spec::D_OUT, u);
+      continue;
+    }
+    for (int64_t t0 = beg; t0 < end; t0 += FT_TE, ++it) {
+      const int cnt = (int)((end - t0 < FT_TE) ? (end - t0) : FT_TE);
+      const uint32_t buf = it & 1;
+      mbar_wait(&S.acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < cnt; c0 += 16) {
+        float w[16];
+        {
+          float hh[16], xx[16];
+          ft_tmem_ld16x2(tlane + 256 + buf * 128 + c0, tlane + 256 + buf * 128 + 64 + c0, hh, xx);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = hh[j] + xx[j];
+        }
+        if (c0 + 16 >= cnt) {  // every needed column of this buffer has been read
+          tc_fence_before();
+          mbar_arrive(&S.acc_empty[buf]);
+        }
+        if (P::ACTIVE && a.w_out != nullptr) {
+          float* wo = a.w_out + (t0 + c0) * (int64_t)Spec::W + P::W_OFF + u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < cnt) wo[(int64_t)j * Spec::W] = w[j];
+        }
+#pragma unroll
+        for (int sb = 0; sb < 2; ++sb) {
+          const int e0 = c0 + sb * FT_SUB;
+          if (e0 < cnt) {
+            const uint32_t st = xs % NXS;
+            mbar_wait(&S.x_full[st], (xs / NXS) & 1);
+            if (P::ACTIVE) {
+              const float* xb = xring + (size_t)st * STAGE_FLOATS + P::XS_OFF + u;
+              const float2* yb = reinterpret_cast<const float2*>(xring + (size_t)st * STAGE_FLOATS + FT_SUB * XROW) + P::Y_OFF;
+#pragma unroll
+              for (int q = 0; q < FT_SUB / 2; ++q) {
+                if (e0 + 2 * q < cnt) {
+                  float2 xv[P::N1], yv[P::N2];
+#pragma unroll
+                  for (int i = 0; i < P::N1; ++i)
+                    xv[i] = make_float2(xb[(2 * q) * XROW + i * P::MUL], xb[(2 * q + 1) * XROW + i * P::MUL]);
+#pragma unroll
+                  for (int j = 0; j < P::N2; ++j) yv[j] = yb[q * SD + j];
+                  P::fma(xv, yv, make_float2(w[sb * FT_SUB + 2 * q], w[sb * FT_SUB + 2 * q + 1]), acc);
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.x_empty[st]);
+            ++xs;
+          }
+        }
+      }
+    }
+    if (P::ACTIVE) {
+      P::store(a.out + n * Spec::D_OUT, u, acc);
+#pragma unroll
+      for (int k = 0; k < P::N3; ++k) acc[k] = make_float2(0.f, 0.f);
+    }
+  }
+}
+
+struct FtNullPath {
+  static constexpr bool ACTIVE = false;
+  static constexpr int N1 = 1, N2 = 1, N3 = 0, XS_OFF = 0, Y_OFF = 0, W_OFF = 0, MUL = 32;
+  static __device__ __forceinline__ void fma(const float2*, const float2*, float2, float2*) {}
+  static __device__ __forceinline__ void store(float*, int, const float2*) {}
+  static __device__ __forceinline__ void store_zero(float*, int) {}
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel.  Spec (generated): MUL, S, D_IN, D_OUT, W, NSLICE, XROW, NXS, seg tables, consume(slice, quad, ...)
+// ---------------------------------------------------------------------------------------------------------
+template <class Spec>
+__global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const FusedFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t ft_smem_raw[];
+  FtSmem& S = *reinterpret_cast<FtSmem*>(ft_smem_raw);
+  float* xring = reinterpret_cast<float*>(ft_smem_raw + ((sizeof(FtSmem) + 127) / 128) * 128);
+  constexpr int NXS = Spec::NXS, XROW = Spec::XROW, SD = Spec::S;
+  constexpr int STAGE_FLOATS = FT_SUB * (XROW + SD);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&S.a_full[s], 128); mbar_init(&S.a_done[s], 1);
+      mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 128);
+    }
+    for (int s = 0; s < NXS; ++s) { mbar_init(&S.x_full[s], 128); mbar_init(&S.x_empty[s], 4); }
+    mbar_init(&S.w_full, 128);
+    fence_barrier_init();
+    // which slice / node range
+    int s = 0;
+    while (s + 1 < Spec::NSLICE && (int)blockIdx.x >= a.slice_cta0[s + 1]) ++s;
+    const int j = (int)blockIdx.x - a.slice_cta0[s], ns = a.slice_cta0[s + 1] - a.slice_cta0[s];
+    S.slice = s;
+    const int64_t t_lo = (a.E * (int64_t)j) / ns, t_hi = (a.E * (int64_t)(j + 1)) / ns;
+    S.n0 = (j == 0) ? 0 : ft_lower_bound(a.row_ptr, a.N, t_lo);
+    S.n1 = (j + 1 == ns) ? a.N : ft_lower_bound(a.row_ptr, a.N, t_hi);
+  }
+  if (warp == 8) tmem_alloc(&S.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+  const int slice = S.slice;
+  const int64_t n0 = S.n0, n1 = S.n1;
+  const int ksteps = a.K / 8;
+  // TMEM columns: [0,128) W hi, [128,256) W lo, per accumulator buffer b: [256 + 128 b, +64) hi*hi, [+64, +128) cross terms
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ================= consumers: upload the slice's weights, then the tensor product ====================
+    {
+      const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+      const float* wrow = a.wprep + ((int64_t)slice * 2 * 128 + warp * 32 + lane) * FT_KMAX;
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {
+#pragma unroll 1
+        for (int c = 0; c < FT_KMAX / 32; ++c) {
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(wrow + (int64_t)part * 128 * FT_KMAX + c * 32 + q * 4));
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+          }
+          ft_tmem_st32(tlane + part * 128 + c * 32, v);
+        }
+      }
+      ft_tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&S.w_full);
+    }
+    Spec::consume(slice, warp, lane, a, S, xring, tmem);
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // ================= producers ===========================================================================
+    const int pw = warp - 4, ptid = tid - 128;
+    const int r8 = lane & 7, kq = lane >> 3;
+    const int kgroups = ksteps * 2;  // 16-byte k-groups the MMAs read
+    // slice staging table: segment s copies `len` floats from x row offset `goff` to stage row offset `soff`
+    const int nseg = Spec::seg_count(slice);
+    int ppe = 0;  // 16-byte pieces per edge
+    for (int s = 0; s < nseg; ++s) ppe += Spec::seg_len(slice, s) / 4;
+    auto issue_h = [&](uint32_t it, int64_t t0, int cnt) {
+      float* dst = S.hraw[it & 1];
+      const int nrg = ((cnt + 15) & ~15) / 8;  // 8-row groups the MMA reads (N rounded up to 16)
+#pragma unroll 1
+      for (int kb = pw; kb * 4 < kgroups; kb += 4) {
+        const int kg = kb * 4 + kq, k = kg * 4;
+#pragma unroll 1
+        for (int rg = 0; rg < nrg; ++rg) {
+          const int m = rg * 8 + r8;
+          const bool in = m < cnt;
+          cp_async16(dst + rg * (FT_KMAX / 4 * 32) + kg * 32 + r8 * 4, a.h + (in ? (t0 + m) * a.ldh + k : 0), in ? 16u : 0u);
+        }
+      }
+    };
+    auto lo_pass = [&](uint32_t it, int cnt) {
+      const float* raw = S.hraw[it & 1];
+      float* lo = S.hlo[it & 1];
+      const int nrg = ((cnt + 15) & ~15) / 8;
+#pragma unroll 1
+      for (int kb = pw; kb * 4 < kgroups; kb += 4) {
+        const int kg = kb * 4 + kq;
+#pragma unroll 2
+        for (int rg = 0; rg < nrg; ++rg) {
+          const float4 t = *reinterpret_cast<const float4*>(raw + rg * (FT_KMAX / 4 * 32) + kg * 32 + r8 * 4);
+          *reinterpret_cast<float4*>(lo + rg * (FT_KMAX / 4 * 32) + kg * 32 + r8 * 4) =
+              make_float4(tf32_lo(t.x), tf32_lo(t.y), tf32_lo(t.z), tf32_lo(t.w));
+        }
+      }
+    };
+    uint32_t xs = 0;
+    auto issue_x = [&](int64_t t0, int cnt) {
+      for (int e0 = 0; e0 < cnt; e0 += FT_SUB, ++xs) {
+        const uint32_t st = xs % NXS;
+        if (xs >= (uint32_t)NXS) mbar_wait(&S.x_empty[st], ((xs / NXS) - 1) & 1);
+        float* stage = xring + (size_t)st * STAGE_FLOATS;
+        const int ne = (cnt - e0 < FT_SUB) ? (cnt - e0) : FT_SUB;
+        const int nep = ne + (ne & 1);  // the odd partner of a last single edge is zero-filled
+        for (int p = ptid; p < nep * ppe; p += 128) {
+          const int e = p / ppe;
+          int k = p - e * ppe, s = 0, soff = 0;
+          while (s + 1 < nseg && k >= Spec::seg_len(slice, s) / 4) { k -= Spec::seg_len(slice, s) / 4; soff += Spec::seg_len(slice, s); ++s; }
+          const bool valid = e < ne;
+          const int64_t row = valid ? a.src[t0 + e0 + e] : 0;
+          cp_async16(stage + e * XROW + soff + k * 4, a.x + row * Spec::D_IN + Spec::seg_goff(slice, s) + k * 4, valid ? 16u : 0u);
+        }
+        float* ys = stage + FT_SUB * XROW;  // [pair][S][2]
+        for (int p = ptid; p < nep * SD; p += 128) {
+          const int e = p / SD, j = p - e * SD;
+          const bool valid = e < ne;
+          ft_cp_async4(ys + ((e >> 1) * SD + j) * 2 + (e & 1), a.y + (valid ? (t0 + e0 + e) * SD + j : 0), valid ? 4u : 0u);
+        }
+        ft_cp_async_arrive(&S.x_full[st]);
+      }
+    };
+    // tile walk with the h tile one tile ahead:  group(it) = { x of tile it - 2 ..., h of tile it }
+    struct Tile { int64_t t0; int cnt; bool ok; };
+    int64_t wn = n0, wt = 0;  // walker: node, offset inside the node
+    auto next_tile = [&]() {
+      Tile t; t.ok = false; t.t0 = 0; t.cnt = 0;
+      while (wn < n1) {
+        const int64_t beg = a.row_ptr[wn], end = a.row_ptr[wn + 1];
+        if (beg + wt < end) {
+          t.t0 = beg + wt;
+          t.cnt = (int)((end - t.t0 < FT_TE) ? (end - t.t0) : FT_TE);
+          t.ok = true;
+          wt += FT_TE;
+          if (beg + wt >= end) { ++wn; wt = 0; }
+          return t;
+        }
+        ++wn; wt = 0;
+      }
+      return t;
+    };
+    uint32_t it = 0;
+    Tile cur = next_tile();
+    if (cur.ok) issue_h(0, cur.t0, cur.cnt);
+    cp_async_commit();
+    while (cur.ok) {
+      const Tile nxt = next_tile();
+      if (nxt.ok) {
+        if (it + 1 >= 2) mbar_wait(&S.a_done[(it + 1) & 1], (((it + 1) >> 1) - 1) & 1);  // MMAs of tile it - 1 done
+        issue_h(it + 1, nxt.t0, nxt.cnt);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();  // h of tile `it` (and every older copy) has landed
+      lo_pass(it, cur.cnt);
+      fence_proxy_async();
+      mbar_arrive(&S.a_full[it & 1]);
+      issue_x(cur.t0, cur.cnt);
+      cur = nxt;
+      ++it;
+    }
+    cp_async_wait<0>();
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 8) {
+      // ================= MMA issue ===========================================================================
+      const bool leader = elect_one();
+      constexpr uint32_t SBO = (FT_KMAX / 4) * 128, LBO = 128;
+      const uint64_t dR0 = make_desc(smem_u32(S.hraw[0]), LBO, SBO);
+      const uint64_t dL0 = make_desc(smem_u32(S.hlo[0]), LBO, SBO);
+      constexpr uint32_t STAGE = (FT_TILE_FLOATS * sizeof(float)) >> 4;
+      mbar_wait(&S.w_full, 0);
+      tc_fence_after();
+      uint32_t it = 0;
+      for (int64_t n = n0; n < n1; ++n) {
+        const int64_t beg = a.row_ptr[n], end = a.row_ptr[n + 1];
+        for (int64_t t0 = beg; t0 < end; t0 += FT_TE, ++it) {
+          const int cnt = (int)((end - t0 < FT_TE) ? (end - t0) : FT_TE);
+          const uint32_t buf = it & 1, s = it & 1;
+          const uint32_t idesc = make_idesc(128, (cnt + 15) & ~15);
+          if (it >= 2) { mbar_wait(&S.acc_empty[buf], ((it >> 1) - 1) & 1); tc_fence_after(); }
+          const uint64_t b_hi = dR0 + (uint64_t)(s * STAGE), b_lo = dL0 + (uint64_t)(s * STAGE);
+          const uint32_t d_hh = tmem + 256 + buf * 128, d_x = d_hh + 64;
+          mbar_wait(&S.a_full[s], (it >> 1) & 1);
+          if (leader) {
+            // one k-step = 8 tf32 = 8 TMEM columns of the weights, 2 core matrices (16 descriptor units) of the h rows
+#pragma unroll 4
+            for (int ks = 0; ks < ksteps; ++ks) ft_umma_ts(d_hh, tmem + ks * 8, b_hi + ks * 16, idesc, ks > 0);
+#pragma unroll 4
+            for (int ks = 0; ks < ksteps; ++ks) ft_umma_ts(d_x, tmem + 128 + ks * 8, b_hi + ks * 16, idesc, ks > 0);
+#pragma unroll 4
+            for (int ks = 0; ks < ksteps; ++ks) ft_umma_ts(d_x, tmem + ks * 8, b_lo + ks * 16, idesc, 1);
+            umma_commit(&S.a_done[s]);
+            umma_commit(&S.acc_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+template <class Spec>
+inline size_t ft_smem_bytes() {
+  return ((sizeof(FtSmem) + 127) / 128) * 128 + (size_t)Spec::NXS * FT_SUB * (Spec::XROW + Spec::S) * sizeof(float) + 1024;
+}
+
+}  // namespace

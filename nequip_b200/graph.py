@@ -64,6 +64,11 @@ class GraphedEnergyForces:
         ops.csr_cache.clear()  # the cached CSR lives in the graph's private pool
         self.launches_per_replay = _capi.launch_count() - n0  # nequip_b200 kernels captured (torch's are extra)
         self.replays = 0
+        # the "edges grouped by destination" flag of every replay is copied to pinned host memory right after
+        # the graph and checked when the NEXT replay is issued (or by check_sorted()): an unsorted neighbour
+        # list of the captured shape can therefore never go unnoticed for more than one step
+        self._flag_host = torch.ones(1, dtype=torch.int32).pin_memory()
+        self._flag_event: Optional[torch.cuda.Event] = None
 
     def _run(self):
         d = dict(self.extra)
@@ -81,9 +86,21 @@ class GraphedEnergyForces:
                 raise ValueError(f"GraphedEnergyForces was captured for {k} of shape {tuple(buf.shape)}, got {tuple(src.shape)}")
             buf.copy_(src, non_blocking=True)
 
+    def _verify_previous(self) -> None:
+        if self._flag_event is not None:
+            self._flag_event.synchronize()
+            self._flag_event = None
+            if int(self._flag_host[0]) != 1:
+                raise RuntimeError("GraphedEnergyForces: the previous frame's edge_index was not grouped by "
+                                   "destination -- its energies/forces are invalid; use the eager model call")
+
     def replay(self) -> Dict[str, torch.Tensor]:
+        self._verify_previous()
         self.graph.replay()
         self.replays += 1
+        self._flag_host.copy_(self.sorted_flag, non_blocking=True)
+        self._flag_event = torch.cuda.Event()
+        self._flag_event.record()
         return {"total_energy": self.energy, "forces": self.forces, "edges_sorted": self.sorted_flag}
 
     def __call__(self, data: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
@@ -93,5 +110,6 @@ class GraphedEnergyForces:
 
     def check_sorted(self) -> None:
         """Host-side verification of the in-graph sortedness flag (synchronises)."""
+        self._verify_previous()
         if int(self.sorted_flag.item()) != 1:
             raise RuntimeError("GraphedEnergyForces: edge_index is not grouped by destination; use the eager model call")

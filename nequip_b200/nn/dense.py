@@ -143,16 +143,15 @@ class _RadialMLPGemmFn(torch.autograd.Function):
     def forward(ctx, emb, w1s, fwd: ops.GroupedGemm, bwd: ops.GroupedGemm, W: int):
         E, hid = emb.shape[0], w1s.shape[1]
         fast = emb.shape[1] == 8 and hid == 128  # fused CUDA-core kernels for the K = 8 layer
-        h_lo = None
         if fast:
-            # the hidden kernel also writes the tf32 low part of h, so the GEMM's producers only copy
+            # (no pre-split low part: handing `a_lo` to k_gemm3x collapses its producer pipeline to one
+            # piece in flight -- 1.7x slower in-step, VERDICT r01 / profiles/r01_gemm_roles.txt)
             h = torch.empty((E, hid), dtype=emb.dtype, device=emb.device)
-            h_lo = torch.empty_like(h)
-            ops.mlp_hidden_fwd(emb, w1s, h, h_lo)
+            ops.mlp_hidden_fwd(emb, w1s, h, None)
         else:
             h = torch.nn.functional.silu(torch.mm(emb, w1s))
         out = torch.empty((E, W), dtype=emb.dtype, device=emb.device)
-        fwd.run(h, out, E, a_lo=h_lo)
+        fwd.run(h, out, E)
         ctx.bwd, ctx.w1s, ctx.fast = bwd, w1s, fast
         ctx.save_for_backward(emb)  # the pre-activation is recomputed in the backward (8 FMAs per value)
         return out
@@ -188,3 +187,70 @@ class RadialMLPGemm:
 
     def __call__(self, emb):
         return _RadialMLPGemmFn.apply(emb.contiguous(), self.w1s, self.fwd, self.bwd, self.W)
+
+
+# ---------------------------------------------------------------------------------------
+class _FusedRadialTPFn(torch.autograd.Function):
+    """``out = scatter(TP(x[src], y, silu(emb @ W1 a1) @ W2 a2))`` with the last radial layer fused into the
+    tensor-product kernel (forward: the [E, W] weights are produced in tensor memory and consumed in place;
+    they are written once on the side only when a backward pass will need them)."""
+
+    @staticmethod
+    def forward(ctx, emb, x, y, edge_src, mod: "FusedRadialTP", csr):
+        E, hid = emb.shape[0], mod.w1s.shape[1]
+        if emb.shape[1] == 8 and hid == 128:
+            h = torch.empty((E, hid), dtype=emb.dtype, device=emb.device)
+            ops.mlp_hidden_fwd(emb, mod.w1s, h, None)
+        else:
+            h = torch.nn.functional.silu(torch.mm(emb, mod.w1s))
+        need_bwd = any(ctx.needs_input_grad[:3])
+        out, w = ops.tp_fused_fwd(mod.fw, x, y, h, edge_src, csr, want_w=need_bwd)
+        ctx.mod, ctx.csr = mod, csr
+        if need_bwd:
+            ctx.save_for_backward(emb, x, y, w, edge_src)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        emb, x, y, w, edge_src = ctx.saved_tensors
+        mod = ctx.mod
+        gx, gy, gw = ops.tp_scatter_bwd_raw(mod.plan, x, y, w, edge_src, ctx.csr, gout, need_x=ctx.needs_input_grad[1])
+        gemb = None
+        if ctx.needs_input_grad[0]:
+            E, hid = emb.shape[0], mod.w1s.shape[1]
+            gh = torch.empty((E, hid), dtype=emb.dtype, device=emb.device)
+            mod.bwd.run(gw, gh, E)
+            if emb.shape[1] == 8 and hid == 128:
+                gemb = torch.empty_like(emb)
+                ops.mlp_hidden_bwd(emb, mod.w1s, gh, gemb)
+            else:
+                pre = torch.mm(emb, mod.w1s)
+                gemb = torch.mm(torch.ops.aten.silu_backward(gh, pre), mod.w1s.t())
+        return gemb, gx, (gy if ctx.needs_input_grad[2] else None), None, None, None
+
+
+class FusedRadialTP:
+    """Radial MLP (one hidden layer) + TensorProductScatter of one interaction layer as a single forward kernel
+    (``nqb_tp_fused_fwd``); backward = ``nqb_tp_scatter_bwd`` + the grouped GEMM for ``grad_h`` + the hidden layer."""
+
+    def __init__(self, lin1, lin2, plan: ops.TPPlan, device):
+        self.plan = plan
+        self.w1s = (lin1.weight.detach() * lin1.alpha).contiguous()
+        hid, W = lin2.weight.shape
+        a2 = float(lin2.alpha)
+        self.fw = ops.FusedTPWeights(plan, lin2.weight.detach(), a2, device)
+        self.bwd = ops.GroupedGemm([ops.GemmProblem(0, W, 0, hid, lin2.weight.detach(), scale=a2, transposed=True)], device)
+
+    @staticmethod
+    def supported(lin1, lin2, plan: ops.TPPlan, dtype) -> bool:
+        hid, W = lin2.weight.shape
+        if dtype != torch.float32 or hid > 128 or hid % 8 or W != plan.weight_numel or W % 4:
+            return False
+        return int(ops._capi.lib().nqb_tp_fused_slices(plan.handle)) > 0
+
+    def __call__(self, emb, x, y, edge_dst, edge_src):
+        csr = ops.csr_cache.get(edge_dst.long().contiguous() if edge_dst.dtype != torch.int64 else edge_dst, x.shape[0])
+        if csr.perm is not None:
+            return None  # unsorted neighbour list: the caller uses the unfused kernels (which take the permutation)
+        return _FusedRadialTPFn.apply(emb.contiguous(), x.contiguous(), y.contiguous(), edge_src.long().contiguous(), self, csr)

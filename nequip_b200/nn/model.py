@@ -43,6 +43,9 @@ ATOM_TYPE_KEY = "atom_types"
 TOTAL_ENERGY_KEY = "total_energy"
 PER_ATOM_ENERGY_KEY = "atomic_energy"
 FORCE_KEY = "forces"
+BATCH_KEY = "batch"
+BATCH_PTR_KEY = "ptr"
+NUM_NODES_KEY = "num_atoms"
 
 
 # ---------------------------------------------------------------------------------------
@@ -312,27 +315,30 @@ class InteractionBlock(torch.nn.Module):
                                           hidden_layers_width=radial_mlp_width, nonlinearity="silu")
         self.linear_2 = Linear(irreps_mid.simplify(), fout, layout)
         self.sc = SelfConnection(fin, num_node_attrs, fout, layout) if use_sc else None
-        self.use_tensor_core_mlp = True
         self.use_tensor_cores = True
-        self._prep_mlp = None
+        self.use_fused_radial_tp = True  # SURVEY 8f-1 kernel when the signature has one (mul % 32 == 0, K <= 128)
+        self.strict_fast_path = False
         self._tc_cache = None
 
     def _edge_weights(self, edge_embedding):
-        """Radial MLP.  Depth-1 / width-128 float32 networks whose weights are frozen (inference) run
-        on the tensor cores (tcgen05 3xTF32, nequip_b200/csrc/nqb_mlp.cu); anything else uses the
-        plain torch.mm formulation of the reference (mlp.py:262-268)."""
-        mlp = self.edge_mlp
-        lins = [m for m in mlp.mlp if isinstance(m, ScalarLinearLayer)]
-        frozen = not any(l.weight.requires_grad for l in lins)
-        if (self.use_tensor_core_mlp and frozen and edge_embedding.is_cuda and len(lins) == 2
-                and ops.PreparedRadialMLP.supported(lins[0].in_features, lins[0].out_features, 1,
-                                                    lins[1].out_features, edge_embedding.dtype)):
-            key = (lins[0].weight.data_ptr(), lins[0].weight._version, lins[1].weight.data_ptr(), lins[1].weight._version)
-            if self._prep_mlp is None or self._prep_mlp[0] != key:
-                self._prep_mlp = (key, ops.PreparedRadialMLP(lins[0].weight, float(lins[0].alpha), lins[1].weight,
-                                                             float(lins[1].alpha)))
-            return ops.radial_mlp(edge_embedding, self._prep_mlp[1])
-        return mlp(edge_embedding)
+        """Radial MLP, plain torch.mm formulation of the reference (mlp.py:262-268) -- the path for trainable
+        weights, float64 and unusual shapes; frozen float32 ir_mul models use ``_tensor_core_blocks``."""
+        return self.edge_mlp(edge_embedding)
+
+    def _note_fallback(self, reason: str):
+        """The library (torch.matmul / cuBLAS) formulation is about to run instead of the tcgen05 blocks: say so
+        once per block and reason, or raise when the model was built with ``strict_fast_path=True`` (bench.py,
+        smoke(): a silent library fallback would be timed as if it were the product)."""
+        if getattr(self, "strict_fast_path", False):
+            raise RuntimeError(f"nequip_b200 InteractionBlock: tensor-core fast path unavailable ({reason}) and "
+                               "strict_fast_path=True")
+        seen = self.__dict__.setdefault("_fallback_seen", set())
+        if reason not in seen:
+            seen.add(reason)
+            import warnings
+
+            warnings.warn(f"nequip_b200 InteractionBlock: dense blocks run through torch.matmul (cuBLAS), not the "
+                          f"tcgen05 kernels: {reason}", RuntimeWarning, stacklevel=3)
 
     def forward(self, x, node_attrs, edge_attrs, edge_embedding, edge_index, types=None, type_table=None,
                 n_own: Optional[int] = None, halo=None):
@@ -351,7 +357,23 @@ class InteractionBlock(torch.nn.Module):
             x = tc["lin1"](x)  # 1/sqrt(avg_num_neighbors) folded into the prepared weights
             if halo is not None and not self.is_first_layer:
                 x = halo(x)
-            w = tc["mlp"](edge_embedding) if tc["mlp"] is not None else self._edge_weights(edge_embedding)
+            if tc["fused"] is not None and self.use_fused_radial_tp:
+                # one kernel: last radial layer (tcgen05, weights resident in tensor memory) -> TP -> scatter
+                y = tc["fused"](edge_embedding, x, edge_attrs, edge_index[0], edge_index[1])
+                if y is not None:
+                    x = y
+                    if n_own is not None:
+                        x = x[:n_own]
+                    x = tc["lin2"](x)
+                    if tc["sc"] is not None:
+                        x = tc["sc"](x_in, types, x)
+                    return x
+            if tc["mlp"] is not None:
+                w = tc["mlp"](edge_embedding)
+            else:
+                self._note_fallback("radial MLP shape not supported by the grouped GEMM (needs one hidden layer, "
+                                    "widths multiples of 4)")
+                w = self._edge_weights(edge_embedding)
             x = self.tp_scatter(x=x, edge_attr=edge_attrs, edge_weight=w, edge_dst=edge_index[0], edge_src=edge_index[1])
             if n_own is not None:
                 x = x[:n_own]
@@ -378,20 +400,28 @@ class InteractionBlock(torch.nn.Module):
         (nequip_b200/nn/dense.py); None when not applicable (training, float64, mul_ir, odd multiplicities)."""
         from . import dense
 
-        if not (self.use_tensor_cores and x.is_cuda and x.dtype == torch.float32 and self.layout == "ir_mul"):
+        if not self.use_tensor_cores or not x.is_cuda:
+            return None
+        if x.dtype != torch.float32 or self.layout != "ir_mul":
+            self._note_fallback(f"dtype {x.dtype} / layout {self.layout} (needs float32, ir_mul)")
             return None
         if any(p.requires_grad for p in self.parameters()) or (type_table is not None and type_table.requires_grad):
+            self._note_fallback("parameters require grad (training); freeze them for the inference path")
             return None
         if self.sc is not None and (types is None or type_table is None):
+            self._note_fallback("self-connection needs atom types + type table")
             return None
         key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (
             (type_table.data_ptr(), type_table._version) if type_table is not None else ())
         if self._tc_cache is not None and self._tc_cache[0] == key:
+            if self._tc_cache[1] is None:
+                self._note_fallback("a multiplicity is not a multiple of 4")
             return self._tc_cache[1]
         ok = dense.IrrepsLinearGemm.supported(self.linear_1) and dense.IrrepsLinearGemm.supported(self.linear_2)
         if self.sc is not None:
             ok = ok and dense.SelfConnectionGemm.supported(self.sc)
         if not ok:
+            self._note_fallback("a multiplicity is not a multiple of 4")
             self._tc_cache = (key, None)
             return None
         dev = x.device
@@ -399,7 +429,11 @@ class InteractionBlock(torch.nn.Module):
         mlp = None
         if len(lins) == 2 and dense.RadialMLPGemm.supported(lins[0], lins[1], x.dtype):
             mlp = dense.RadialMLPGemm(lins[0], lins[1], dev)
+        fused = None
+        if len(lins) == 2 and dense.FusedRadialTP.supported(lins[0], lins[1], self.tp_scatter._plan, x.dtype):
+            fused = dense.FusedRadialTP(lins[0], lins[1], self.tp_scatter._plan, dev)
         blocks = dict(
+            fused=fused,
             lin1=dense.IrrepsLinearGemm(self.linear_1, dev, extra_scale=float(self.norm_const)),
             lin2=dense.IrrepsLinearGemm(self.linear_2, dev),
             sc=dense.SelfConnectionGemm(self.sc, type_table, dev) if self.sc is not None else None,
@@ -436,7 +470,7 @@ class NequIPEnergyModel(torch.nn.Module):
                  radial_mlp_width: int = 128, num_bessels: int = 8, polynomial_cutoff_p: float = 6.0,
                  avg_num_neighbors: float = 1.0, per_type_energy_scales: Optional[Sequence[float]] = None,
                  per_type_energy_shifts: Optional[Sequence[float]] = None, model_dtype=torch.float32,
-                 seed: int = 123, node_layout: str = "ir_mul"):
+                 seed: int = 123, node_layout: str = "ir_mul", strict_fast_path: bool = False):
         super().__init__()
         self.r_max, self.l_max, self.num_bessels, self.poly_p = float(r_max), l_max, num_bessels, float(polynomial_cutoff_p)
         self.model_dtype = model_dtype
@@ -467,10 +501,42 @@ class NequIPEnergyModel(torch.nn.Module):
             self.readout = ScalarMLPFunction(prev.dim, 1, hidden_layers_depth=0)
         finally:
             torch.set_default_dtype(prev_default)
-        sc = None if per_type_energy_scales is None else torch.as_tensor(per_type_energy_scales, dtype=torch.float64).reshape(-1, 1)
-        sh = None if per_type_energy_shifts is None else torch.as_tensor(per_type_energy_shifts, dtype=torch.float64).reshape(-1, 1)
-        self.register_buffer("scales", sc if sc is not None else torch.empty(0, dtype=torch.float64))
-        self.register_buffer("shifts", sh if sh is not None else torch.empty(0, dtype=torch.float64))
+        # PerTypeScaleShift (atomwise.py:236-284): a float or a one-element list applies to every type
+        # (the reference's scales_shortcut / shifts_shortcut); otherwise one value per type
+        def table(v, what):
+            if v is None:
+                return torch.empty(0, dtype=torch.float64)
+            t = torch.as_tensor(v, dtype=torch.float64).reshape(-1)
+            if t.numel() == 1:
+                t = t.expand(ntypes).clone()
+            if t.numel() != ntypes:
+                raise ValueError(f"{what}: expected a scalar or {ntypes} values (one per type), got {t.numel()}")
+            return t.reshape(-1, 1)
+
+        self.register_buffer("scales", table(per_type_energy_scales, "per_type_energy_scales"))
+        self.register_buffer("shifts", table(per_type_energy_shifts, "per_type_energy_shifts"))
+        self.set_strict_fast_path(strict_fast_path)
+
+    def set_strict_fast_path(self, on: bool = True):
+        """Raise instead of warning when an interaction block cannot use the tcgen05 dense blocks."""
+        for layer in self.layers:
+            layer.conv.strict_fast_path = bool(on)
+        return self
+
+    @staticmethod
+    def _reduce_energy(e_atom: torch.Tensor, data: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """AtomwiseReduce (atomwise.py:92-113): per-graph sum -> [num_graphs, 1]; one frame without ``batch``."""
+        batch = data.get(BATCH_KEY)
+        if batch is None:
+            return e_atom.sum(dim=0, keepdim=True)
+        if NUM_NODES_KEY in data:
+            ng = int(data[NUM_NODES_KEY].numel())
+        elif BATCH_PTR_KEY in data:
+            ng = int(data[BATCH_PTR_KEY].numel()) - 1
+        else:
+            ng = int(batch.max().item()) + 1 if batch.numel() else 0
+        out = torch.zeros((ng, 1), dtype=e_atom.dtype, device=e_atom.device)
+        return out.index_add_(0, batch.view(-1).long(), e_atom)
 
     # the energy part (SequentialGraphNetwork order of nequip_models.py:288-399)
     def energy(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -493,7 +559,7 @@ class NequIPEnergyModel(torch.nn.Module):
         if self.shifts.numel():
             e_atom = e_atom + self.shifts[types]
         data[PER_ATOM_ENERGY_KEY] = e_atom
-        data[TOTAL_ENERGY_KEY] = e_atom.sum(dim=0, keepdim=True)
+        data[TOTAL_ENERGY_KEY] = self._reduce_energy(e_atom, data)
         return data
 
     def energy_owned(self, data: Dict[str, torch.Tensor], n_own: int, halo) -> torch.Tensor:

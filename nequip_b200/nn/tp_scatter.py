@@ -78,12 +78,22 @@ class B200TensorProductScatter(_Base):
         # is used between our own kernels
         import dataclasses
 
-        gen_options = dataclasses.replace(gen_options or GenOptions(), layout=layout)
+        self._gen_options = dataclasses.replace(gen_options or GenOptions(), layout=layout)
         self.layout = layout
-        self._plan = ops.get_plan(
-            Irreps(feature_irreps_in), Irreps(irreps_edge_attr), Irreps(irreps_mid), instructions, gen_options
-        )
-        self.weight_numel = self._plan.weight_numel
+        # the signature is pure host logic; the kernel library is bound on first use, so that constructing a
+        # model (e.g. to obtain a state dict for the CPU reference arm of bench.py) loads no native code
+        from ..codegen import TPSignature
+
+        self._sig = TPSignature(Irreps(feature_irreps_in), Irreps(irreps_edge_attr), Irreps(irreps_mid), list(instructions))
+        self.weight_numel = self._sig.weight_numel
+        self._plan_obj = None
+
+    @property
+    def _plan(self):
+        if self._plan_obj is None:
+            s = self._sig
+            self._plan_obj = ops.get_plan(s.irreps_in1, s.irreps_in2, s.irreps_out, s.instructions, self._gen_options)
+        return self._plan_obj
 
     def forward(self, x, edge_attr, edge_weight, edge_dst, edge_src):
         # explicit cast to account for AMP (as the OpenEquivariance subclass does)

@@ -261,6 +261,97 @@ def tp_scatter(plan: TPPlan, x, edge_attr, edge_weight, edge_dst, edge_src, csr:
 
 
 # ---------------------------------------------------------------------------------------
+# fused last radial-MLP layer + TP + scatter (forward) -- nqb_tp_fused_fwd
+# ---------------------------------------------------------------------------------------
+class FusedTPWeights:
+    """Second-layer radial-MLP weights ``W2 [K, W]`` (times ``alpha2``) permuted into the slice order of the
+    signature's fused kernel, split hi/lo and laid out for tensor memory (once per model), plus the split of
+    the grid (one CTA per SM) over the slices in proportion to their cost."""
+
+    def __init__(self, plan: TPPlan, W2: torch.Tensor, alpha2: float, device):
+        from .codegen import TPGenerator
+
+        L = _capi.lib()
+        self.plan = plan
+        lay = TPGenerator(plan.sig, plan.opts).fused_layout()
+        nslice = int(L.nqb_tp_fused_slices(plan.handle))
+        if lay is None or nslice == 0 or nslice != len(lay["slices"]):
+            raise RuntimeError("FusedTPWeights: this signature has no fused kernel")
+        K, W = int(W2.shape[0]), int(W2.shape[1])
+        if W != plan.weight_numel or K > 128 or K % 8:
+            raise ValueError(f"FusedTPWeights: W2 must be [K <= 128 (multiple of 8), {plan.weight_numel}], got {tuple(W2.shape)}")
+        self.K, self.nslice = K, nslice
+        cols = torch.tensor(lay["cols"], dtype=torch.long, device=device)
+        W2d = W2.detach().to(device=device, dtype=torch.float32)
+        Wp = torch.zeros((K, cols.numel()), dtype=torch.float32, device=device)
+        ok = cols >= 0
+        Wp[:, ok] = W2d[:, cols[ok]]
+        self.prepared = torch.empty(int(L.nqb_gemm_t_prepared_floats(K, Wp.shape[1])), dtype=torch.float32, device=device)
+        _capi.check(L.nqb_gemm_t_prepare(_ptr(Wp), Wp.shape[1], K, Wp.shape[1], 0, float(alpha2), _ptr(self.prepared),
+                                         _stream()), "nqb_gemm_t_prepare")
+        G = torch.cuda.get_device_properties(device).multi_processor_count
+        self.cta0, self.nctas = self.split_grid(lay["cost"], G)
+        self.cta0_dev = torch.tensor(self.cta0, dtype=torch.int32, device=device)
+
+    @staticmethod
+    def split_grid(cost, G: int):
+        """CTAs per slice proportional to cost (every slice gets at least one); returns (prefix, total)."""
+        S = len(cost)
+        n = [1] * S
+        for _ in range(max(0, G - S)):
+            i = max(range(S), key=lambda j: cost[j] / n[j])
+            n[i] += 1
+        pre = [0]
+        for v in n:
+            pre.append(pre[-1] + v)
+        return pre, pre[-1]
+
+
+def tp_fused_fwd(fw: FusedTPWeights, x: torch.Tensor, y: torch.Tensor, h: torch.Tensor, edge_src: torch.Tensor,
+                 csr: EdgeCSR, want_w: bool):
+    """``out [N, D_mid]`` (and the per-edge weights ``w [E, W]`` when ``want_w``) of the fused kernel."""
+    _require_cuda(x, y, h, edge_src)
+    plan = fw.plan
+    if csr.perm is not None:
+        raise RuntimeError("tp_fused_fwd: edges must be grouped by destination (no permutation)")
+    if x.dtype != torch.float32 or y.dtype != torch.float32 or h.dtype != torch.float32:
+        raise TypeError("tp_fused_fwd: float32 only")
+    N, E = x.shape[0], edge_src.numel()
+    if x.shape[1] != plan.d_in or tuple(y.shape) != (E, plan.s_dim) or h.shape[0] != E or h.shape[1] != fw.K:
+        raise ValueError("tp_fused_fwd: shape mismatch")
+    x, y, h = x.contiguous(), y.contiguous(), h.contiguous()
+    out = torch.empty((N, plan.d_out), dtype=torch.float32, device=x.device)
+    w = torch.empty((E, plan.weight_numel), dtype=torch.float32, device=x.device) if want_w else None
+    _capi.check(
+        _capi.lib().nqb_tp_fused_fwd(plan.handle, _ptr(x), _ptr(y), _ptr(h), h.stride(0), fw.K, _ptr(fw.prepared),
+                                     _ptr(csr.row_ptr), _ptr(edge_src), N, E, _ptr(out), _ptr(w), _ptr(fw.cta0_dev),
+                                     int(fw.nctas), _stream()),
+        "nqb_tp_fused_fwd",
+    )
+    return out, w
+
+
+def tp_scatter_bwd_raw(plan: TPPlan, x, y, w, edge_src, csr: EdgeCSR, gout, need_x: bool = True):
+    """Backward kernels of the fused TP+scatter on raw tensors: (grad_x or None, grad_y, grad_w)."""
+    L = _capi.lib()
+    N, E = x.shape[0], edge_src.numel()
+    gx = torch.zeros_like(x) if need_x else None
+    gy = torch.zeros_like(y)
+    gw = torch.empty_like(w)
+    if N > 0 and E > 0:
+        gout = gout.contiguous()
+        _capi.check(
+            L.nqb_tp_scatter_bwd(plan.handle, _DT[x.dtype], _ptr(x), _ptr(y), _ptr(w), _ptr(csr.row_ptr),
+                                 _ptr(csr.perm), _ptr(edge_src), _ptr(gout), N, E, _ptr(gx), _ptr(gy), _ptr(gw),
+                                 _stream()),
+            "nqb_tp_scatter_bwd",
+        )
+    elif E == 0:
+        gw.zero_()
+    return gx, gy, gw
+
+
+# ---------------------------------------------------------------------------------------
 # spherical harmonics / edge embedding
 # ---------------------------------------------------------------------------------------
 class _SHFn(torch.autograd.Function):
@@ -348,71 +439,6 @@ def edge_embed(pos, edge_index, shift=None, cell=None, *, lmax: int, num_bessel:
         cell = cell.double().reshape(3, 3).contiguous()
     return _EdgeEmbedFn.apply(pos, edge_index, shift, cell, int(lmax), int(num_bessel), float(r_max),
                               float(poly_p), float(prefactor), out_dtype)
-
-
-# ---------------------------------------------------------------------------------------
-# radial MLP on the tensor cores (tcgen05, 3xTF32)
-# ---------------------------------------------------------------------------------------
-class PreparedRadialMLP:
-    """Second-layer weights of a depth-1 radial MLP, scaled and laid out for the MMA tiles.
-    Inference-only: the weights are treated as constants (no parameter gradients)."""
-
-    HIDDEN = 128
-    NUM_BESSEL = 8
-
-    def __init__(self, W1: torch.Tensor, alpha1: float, W2: torch.Tensor, alpha2: float):
-        _require_cuda(W1, W2)
-        if W1.dtype != torch.float32 or W2.dtype != torch.float32:
-            raise TypeError("PreparedRadialMLP: float32 weights only")
-        if tuple(W1.shape) != (self.NUM_BESSEL, self.HIDDEN) or W2.shape[0] != self.HIDDEN or W2.shape[1] % 32 != 0:
-            raise ValueError(f"PreparedRadialMLP: unsupported shapes {tuple(W1.shape)} / {tuple(W2.shape)}")
-        L = _capi.lib()
-        self.W = int(W2.shape[1])
-        self.w1s = (W1.detach() * alpha1).contiguous()
-        nfl = int(L.nqb_mlp_prepared_bytes(self.W)) // 4
-        self.prep_fwd = torch.empty(nfl, dtype=torch.float32, device=W2.device)
-        self.prep_bwd = torch.empty(nfl, dtype=torch.float32, device=W2.device)
-        W2c = W2.detach().contiguous()
-        _capi.check(L.nqb_mlp_prepare(_ptr(W2c), float(alpha2), self.HIDDEN, self.W, _ptr(self.prep_fwd),
-                                      _ptr(self.prep_bwd), _stream()), "nqb_mlp_prepare")
-
-    @staticmethod
-    def supported(num_bessel: int, hidden: int, depth: int, W: int, dtype) -> bool:
-        return num_bessel == 8 and hidden == 128 and depth == 1 and W % 32 == 0 and dtype == torch.float32
-
-
-class _RadialMLPFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, emb, prep: PreparedRadialMLP):
-        L = _capi.lib()
-        E = emb.shape[0]
-        out = torch.empty((E, prep.W), dtype=torch.float32, device=emb.device)
-        _capi.check(L.nqb_mlp_fwd(_ptr(emb), _ptr(prep.w1s), _ptr(prep.prep_fwd), E, prep.NUM_BESSEL, prep.HIDDEN,
-                                  prep.W, _ptr(out), _stream()), "nqb_mlp_fwd")
-        ctx.prep = prep
-        ctx.save_for_backward(emb)
-        return out
-
-    @staticmethod
-    @torch.autograd.function.once_differentiable
-    def backward(ctx, gw):
-        (emb,) = ctx.saved_tensors
-        prep = ctx.prep
-        L = _capi.lib()
-        E = emb.shape[0]
-        gemb = torch.empty_like(emb)
-        gw = gw.contiguous()
-        _capi.check(L.nqb_mlp_bwd(_ptr(emb), _ptr(prep.w1s), _ptr(prep.prep_bwd), _ptr(gw), E, prep.NUM_BESSEL,
-                                  prep.HIDDEN, prep.W, _ptr(gemb), _stream()), "nqb_mlp_bwd")
-        return gemb, None
-
-
-def radial_mlp(emb: torch.Tensor, prep: PreparedRadialMLP) -> torch.Tensor:
-    """``edge_weight = silu(emb @ W1 a1) @ (W2 a2)`` -> ``[E, W]`` float32."""
-    _require_cuda(emb)
-    if emb.dtype != torch.float32 or emb.dim() != 2 or emb.shape[1] != prep.NUM_BESSEL:
-        raise ValueError("radial_mlp: emb must be float32 [E, 8]")
-    return _RadialMLPFn.apply(emb.contiguous(), prep)
 
 
 # ---------------------------------------------------------------------------------------

@@ -221,3 +221,49 @@ def test_weighted_cta_split_covers_the_grid(monkeypatch):
     # uniform launch: even split (None)
     rows_u = [[0, 0, 0, -1, 128, 1728, 128, 1728, 4, 14, 0, 0]]
     assert ops.GroupedGemm._weighted_split(rows_u, "cuda") == (None, 0)
+
+
+def test_per_type_scale_shift_accepts_scalar_and_per_type_tables():
+    """PerTypeScaleShift (atomwise.py:236-284): a float / one-element list broadcasts over the types."""
+    from nequip_b200.nn.model import NequIPEnergyModel
+
+    kw = dict(r_max=4.0, type_names=["H", "O", "C"], l_max=1, num_layers=2, num_features=4, radial_mlp_width=8)
+    m = NequIPEnergyModel(per_type_energy_scales=2.5, per_type_energy_shifts=[-1.0], **kw)
+    assert m.scales.shape == (3, 1) and torch.all(m.scales == 2.5) and torch.all(m.shifts == -1.0)
+    types = torch.tensor([0, 2, 1, 2])
+    assert m.scales[types].shape == (4, 1)  # indexable by any type id (was out of bounds for a [1,1] table)
+    m = NequIPEnergyModel(per_type_energy_scales=[1.0, 2.0, 3.0], **kw)
+    assert m.scales.view(-1).tolist() == [1.0, 2.0, 3.0] and m.shifts.numel() == 0
+    with pytest.raises(ValueError):
+        NequIPEnergyModel(per_type_energy_scales=[1.0, 2.0], **kw)
+
+
+def test_total_energy_is_reduced_per_graph():
+    """AtomwiseReduce (atomwise.py:92-113): [num_graphs, 1] for batched input, [1, 1] for a single frame."""
+    from nequip_b200.nn.model import NequIPEnergyModel
+
+    e = torch.arange(6, dtype=torch.float64).view(6, 1)
+    assert NequIPEnergyModel._reduce_energy(e, {}).tolist() == [[15.0]]
+    batch = torch.tensor([0, 0, 1, 1, 1, 2])
+    out = NequIPEnergyModel._reduce_energy(e, {"batch": batch, "ptr": torch.tensor([0, 2, 5, 6])})
+    assert out.tolist() == [[1.0], [9.0], [5.0]]
+    out = NequIPEnergyModel._reduce_energy(e, {"batch": batch, "num_atoms": torch.tensor([2, 3, 1, 0])})
+    assert out.shape == (4, 1) and out[3, 0] == 0
+
+
+def test_model_construction_loads_no_native_code_and_strict_flag_propagates():
+    """bench.py's CPU reference arm builds the model only for its state dict: that must not dlopen the kernels."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from nequip_b200.nn.model import NequIPEnergyModel\n"
+            "m = NequIPEnergyModel(r_max=4.0, type_names=['A'], l_max=2, num_layers=2, num_features=8, radial_mlp_width=16,"
+            " strict_fast_path=True)\n"
+            "assert all(l.conv.strict_fast_path for l in m.layers)\n"
+            "sd = m.state_dict()\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libnqb' not in maps and 'nqbspec' not in maps, 'native kernels were loaded'\n"
+            "print('ok')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

@@ -1,11 +1,13 @@
-"""GPU parity of the tensor-core radial MLP (tcgen05 kind::tf32, 3xTF32 split) against the fp64
-restatement of ScalarMLPFunction (nequip/nn/mlp.py:80-195, 262-268)."""
+"""GPU parity of the radial MLP on the product path (CUDA-core hidden layer k_hidden_fwd/bwd + grouped
+tcgen05 3xTF32 GEMM, nequip_b200/nn/dense.py RadialMLPGemm) against the fp64 restatement of
+ScalarMLPFunction (nequip/nn/mlp.py:80-195, 262-268)."""
 import math
 
 import pytest
 import torch
 
-from nequip_b200 import ops
+from nequip_b200.nn import dense
+from nequip_b200.nn.model import ScalarLinearLayer
 
 pytestmark = pytest.mark.gpu
 
@@ -28,9 +30,13 @@ def test_radial_mlp_forward_backward(E, W):
     ref = _ref(emb_r, W1, a1, W2, a2)
     (gref,) = torch.autograd.grad(ref, emb_r, gw.double())
 
-    prep = ops.PreparedRadialMLP(W1.cuda(), a1, W2.cuda(), a2)
+    l1, l2 = ScalarLinearLayer(8, 128, a1).cuda(), ScalarLinearLayer(128, W, a2).cuda()
+    with torch.no_grad():
+        l1.weight.copy_(W1)
+        l2.weight.copy_(W2)
+    mlp = dense.RadialMLPGemm(l1, l2, "cuda")
     emb_k = emb.cuda().requires_grad_(True)
-    out = ops.radial_mlp(emb_k, prep)
+    out = mlp(emb_k)
     torch.cuda.synchronize()
     err = (out.detach().cpu().double() - ref.detach()).abs().max().item()
     scale = ref.detach().abs().max().item()
@@ -39,6 +45,5 @@ def test_radial_mlp_forward_backward(E, W):
     torch.cuda.synchronize()
     gerr = (gk.cpu().double() - gref).abs().max().item()
     gscale = gref.abs().max().item()
-    # the fused backward accumulates K = W (up to 2176) on ONE TMEM accumulator: ~3e-8 truncation bias per
-    # accumulate step (see nqb_gemm.cu for the segmented variant that removes it)
-    assert gerr <= 3e-5 * gscale + 1e-6, (gerr, gscale)
+    # segmented accumulation (K = W up to 2176 in 320-wide segments): fp32-GEMM class error
+    assert gerr <= 5e-6 * gscale + 1e-6, (gerr, gscale)

@@ -77,31 +77,24 @@ def main():
         del gout, gy, gw, gx
         if not args.skip_mlp:
             lins = [m for m in layer.conv.edge_mlp.mlp if isinstance(m, ScalarLinearLayer)]
-            if len(lins) == 2 and ops.PreparedRadialMLP.supported(lins[0].in_features, lins[0].out_features, 1,
-                                                                   lins[1].out_features, torch.float32):
-                prep = ops.PreparedRadialMLP(lins[0].weight, float(lins[0].alpha), lins[1].weight, float(lins[1].alpha))
+            from nequip_b200.nn import dense
+
+            if len(lins) == 2 and dense.RadialMLPGemm.supported(lins[0], lins[1], torch.float32):
+                mlp = dense.RadialMLPGemm(lins[0], lins[1], dev)
                 emb = torch.rand(E, 8, device=dev, generator=g)
                 with torch.no_grad():
-                    ms = timeit(lambda: ops.radial_mlp(emb, prep), args.reps)
+                    ms = timeit(lambda: mlp(emb), args.reps)
                     ref = torch.nn.functional.silu(emb.double() @ (lins[0].weight.double() * lins[0].alpha.double())) @ (
                         lins[1].weight.double() * lins[1].alpha.double())
-                    out = ops.radial_mlp(emb, prep)
+                    out = mlp(emb)
                     err = float((out.double() - ref).abs().max() / ref.abs().max())
                     del ref, out
                 W = sig.weight_numel
                 flops = 2.0 * E * 128 * W
-                print(json.dumps({"kernel": "mlp_fwd", "layer": li, "W": W, "ms": round(ms, 4), "out_GB": round(E * W * 4 / 1e9, 3),
-                                  "GBps_out": round(E * W * 4 / ms / 1e6, 1), "TFLOPs_fp32_equiv": round(flops / ms / 1e9, 1),
-                                  "rel_err": err}))
-                gemb = torch.empty_like(emb)
-
-                def mb():
-                    ops._capi.check(L.nqb_mlp_bwd(emb.data_ptr(), prep.w1s.data_ptr(), prep.prep_bwd.data_ptr(), w.data_ptr(), E,
-                                                  8, 128, W, gemb.data_ptr(), torch.cuda.current_stream().cuda_stream), "mlp_bwd")
-
-                ms = timeit(mb, args.reps)
-                print(json.dumps({"kernel": "mlp_bwd", "layer": li, "W": W, "ms": round(ms, 4),
-                                  "GBps_in": round(E * W * 4 / ms / 1e6, 1), "TFLOPs_fp32_equiv": round(flops / ms / 1e9, 1)}))
+                print(json.dumps({"kernel": "mlp_fwd (hidden + grouped GEMM)", "layer": li, "W": W, "ms": round(ms, 4),
+                                  "out_GB": round(E * W * 4 / 1e9, 3), "GBps_out": round(E * W * 4 / ms / 1e6, 1),
+                                  "TFLOPs_fp32_equiv": round(flops / ms / 1e9, 1), "rel_err": err}))
+                gemb = None
                 # torch reference timing (cuBLAS fp32 SIMT)
                 with torch.no_grad():
                     W1 = lins[0].weight * lins[0].alpha
