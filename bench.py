@@ -237,9 +237,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="li3po4_10k_l2_f64", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--decomp", default="frames", choices=["frames", "halo"],
-                    help="N>1: 'frames' = one independent frame per GPU (the reference's DDP axis); 'halo' = ONE frame "
-                         "of N x atoms_per_gpu atoms, slab-partitioned, per-layer NCCL halo exchange + energy/force all-reduce")
+    ap.add_argument("--decomp", default="halo", choices=["frames", "halo"],
+                    help="N>1: 'halo' (default) = ONE frame partitioned by atoms into N bricks with halo (ghost) atoms, "
+                         "per-layer NCCL halo exchange, energy all-reduce, ghost forces returned to their owners -- the "
+                         "north_star partition; 'frames' = one independent frame per GPU (the reference's DDP axis)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="halo mode: 'weak' = the frame grows with N (N x the workload's atoms, box elongated along x); "
+                         "'strong' = the workload's own frame split N ways")
     ap.add_argument("--no-graph", action="store_true", help="eager step (no CUDA-graph replay)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one warm-up step, then ONE step between cudaProfilerStart/Stop (for ncu "
@@ -272,19 +276,18 @@ def main():
 
     halo_mode = world > 1 and args.decomp == "halo"
     if halo_mode:
-        # ONE frame of world x (22^3) atoms, elongated along x, slab decomposition (weak scaling)
         from nequip_b200 import parallel as P
+        import numpy as np
 
         kind, ns, mk = WORKLOADS[args.workload]
         pr = D.PRESETS[kind]
-        import numpy as np
-
         a = (1.0 / pr["density"]) ** (1.0 / 3.0)
+        nx = ns * world if args.scaling == "weak" else ns  # weak: ONE frame of world x (ns^3) atoms, elongated along x
         rng = np.random.default_rng(0)
-        gx, gy = np.arange(ns * world, dtype=np.float64), np.arange(ns, dtype=np.float64)
+        gx, gy = np.arange(nx, dtype=np.float64), np.arange(ns, dtype=np.float64)
         zz, yy, xx = np.meshgrid(gy, gy, gx, indexing="ij")
         pos_np = (np.stack([xx.ravel(), yy.ravel(), zz.ravel()], 1) + 0.5 + rng.uniform(-0.22, 0.22, (xx.size, 3))) * a
-        cell_np = np.diag([ns * world * a, ns * a, ns * a])
+        cell_np = np.diag([nx * a, ns * a, ns * a])
         ratios = np.asarray(pr["ratios"], dtype=np.float64)
         types_np = np.random.default_rng(1).choice(len(ratios), size=pos_np.shape[0], p=ratios / ratios.sum())
         ei_np, sh_np = D.neighbor_list(pos_np, cell_np, R_MAX)
@@ -292,7 +295,8 @@ def main():
                 "atom_types": torch.from_numpy(types_np.astype(np.int64)), "edge_index": torch.from_numpy(ei_np),
                 "edge_cell_shift": torch.from_numpy(sh_np)}
         meta = dict(type_names=list(pr["type_names"]), avg_num_neighbors=float(ei_np.shape[1]) / pos_np.shape[0])
-        owner = P.slab_owner(full["pos"], world)
+        grid = P.brick_grid(world, [nx * a, ns * a, ns * a], halo=R_MAX)
+        owner = P.brick_owner(full["pos"], grid)
         plan = P.make_plans(full["edge_index"], owner, world)[rank]
         sysd = P.shard_data(full, plan)
         n_total_atoms = pos_np.shape[0]
@@ -312,22 +316,27 @@ def main():
 
     if halo_mode:
         halo = P.HaloExchange(plan, dev)
+    for layer in model.layers:
+        layer.conv.strict_fast_path = True  # a torch.matmul fallback of a dense block must not be timed silently
 
     graphed = None
-    if not halo_mode and not args.no_graph:
-        from nequip_b200.graph import GraphedEnergyForces
+    if not args.no_graph:
+        from nequip_b200.graph import GraphedEnergyForces, GraphedShardedEnergyForces
 
-        graphed = GraphedEnergyForces(model, resident)  # captured once; replayed every step
+        if halo_mode:  # the sharded step incl. its NCCL exchanges as one graph per rank
+            graphed = GraphedShardedEnergyForces(model, resident, plan, halo)
+        else:
+            graphed = GraphedEnergyForces(model, resident)  # captured once; replayed every step
 
     def step_resident():
         if graphed is not None:
             out = graphed.replay()
-            if world > 1:
+            if world > 1 and not halo_mode:
                 e_buf.copy_(out["total_energy"].view(-1))
                 dist.all_reduce(e_buf)
             return out
         if halo_mode:
-            e, f = P.sharded_energy_forces(model, resident, plan, halo)
+            e, f = P.sharded_energy_forces(model, resident, plan, halo, reduce_forces="owner")
             return {"total_energy": e, "forces": f}
         out = model(resident)
         if world > 1:
@@ -335,13 +344,13 @@ def main():
             dist.all_reduce(e_buf)
         return out
 
-    f_host = torch.empty((n_atoms, 3), dtype=torch.float64).pin_memory()
+    f_host = torch.empty((plan.n_own if halo_mode else n_atoms, 3), dtype=torch.float64).pin_memory()
     e_host = torch.empty((1,), dtype=torch.float64).pin_memory()
 
     def step_e2e():
         if graphed is not None:
             out = graphed(host)  # pinned host -> static device buffers (H2D) -> replay
-            if world > 1:
+            if world > 1 and not halo_mode:
                 e_buf.copy_(out["total_energy"].view(-1))
                 dist.all_reduce(e_buf)
             f_host.copy_(out["forces"], non_blocking=True)
@@ -349,7 +358,7 @@ def main():
             return out
         d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
         if halo_mode:
-            e, f = P.sharded_energy_forces(model, d, plan, halo, reduce_forces=False)
+            e, f = P.sharded_energy_forces(model, d, plan, halo, reduce_forces="owner")
             out = {"total_energy": e, "forces": f}
         else:
             out = model(d)
@@ -476,15 +485,17 @@ def main():
             "warmup": args.warmup,
             "ms_per_step": ms_res,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": (args.scaling if halo_mode else "weak"),
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
             "config": {
                 "workload": args.workload,
                 "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges, "r_max": R_MAX, "parity": True, **mk,
-                "parallelism": (f"halo{world}: one {total_atoms}-atom frame in {world} x-slabs, {plan.n_own} owned + "
-                                f"{plan.n_ghost} ghost atoms on rank 0, per-layer NCCL halo exchange" if halo_mode
+                "parallelism": (f"halo{world}: one {total_atoms}-atom frame partitioned by atoms into {grid[0]}x{grid[1]}x{grid[2]} "
+                                f"bricks, {plan.n_own} owned + {plan.n_ghost} ghost atoms on rank 0, per-layer NCCL halo "
+                                f"exchange of ghost features, energy all-reduce, ghost forces reduced to owners ({args.scaling} scaling)"
+                                if halo_mode
                                 else f"dp{world} over frames (one {n_atoms}-atom frame per GPU)"),
                 "launch": ("one CUDA-graph replay per step (nequip_b200/graph.py)" if graphed is not None
                            else "eager launches"),

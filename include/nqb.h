@@ -136,6 +136,26 @@ int nqb_edge_embed_bwd(int lmax, int num_bessel, double r_max, double poly_p, do
                        int out_dtype, const void* grad_y, const void* grad_emb, double* grad_pos,
                        double* grad_vec, nqb_stream_t st);
 
+/* Neighbour list on the device (cell list; full list, both directions, periodic images, no self edge in the home
+ * image) -- replaces the host construction of nequip/data/_nl.py:60-152,292-361 and emits what
+ * SortedNeighborListTransform (nequip/data/transforms/neighborlist.py:120-157) produces: edges sorted by
+ * (centre, neighbour) = the destination CSR of the convolution.  Three calls around two host-side scans
+ * (nequip_b200/ops.py neighbor_list): bins -> [sort atoms by bin] -> counts -> [exclusive scan] -> fill.
+ * cell/inv: 3x3 row-major HOST arrays (rows = lattice vectors, inv = cell^-1); pbc/nbins/search: 3 ints;
+ * lo/width: bounding box of the fractional coordinates in non-periodic directions (NULL if all periodic).
+ * edge vector = pos[j] - pos[i] + shifts @ cell, i = edge_index[0][e] (centre), j = edge_index[1][e]. */
+int nqb_nl_bin(const double* pos, int64_t N, const double* cell_host, const double* inv_host, const int* pbc,
+               const int* nbins, const int* search, const double* lo, const double* width, double r_max,
+               double* wpos /* [N,3] */, int32_t* base /* [N,3] */, int64_t* bin /* [N] */, int32_t* cidx /* [N,3] */,
+               nqb_stream_t st);
+int nqb_nl_count(int64_t N, const double* cell_host, const double* inv_host, const int* pbc, const int* nbins,
+                 const int* search, double r_max, const double* wpos, const int32_t* cidx, const int64_t* order,
+                 const int64_t* bin_start, int64_t* counts /* [N] */, nqb_stream_t st);
+int nqb_nl_fill(int64_t N, int64_t E, const double* cell_host, const double* inv_host, const int* pbc, const int* nbins,
+                const int* search, double r_max, const double* wpos, const int32_t* cidx, const int32_t* base,
+                const int64_t* order, const int64_t* bin_start, const int64_t* row_ptr /* [N+1] */,
+                int64_t* edge_index /* [2,E] */, double* shifts /* [E,3] */, nqb_stream_t st);
+
 /* First radial layer (K = 8, CUDA cores):  h[E,128] = silu(emb[E,8] @ W1s[8,128])  and
  * grad_emb[E,8] = (grad_h * silu'(emb @ W1s)) @ W1s^T  (pre-activation recomputed, nothing saved).
  * Together with nqb_gemm_grouped for the second layer this is ScalarMLPFunction (nequip/nn/mlp.py:80-195). */

@@ -45,6 +45,9 @@ SIGNATURES = {
         _i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "nqb_tp_fused_slices": (_i32, [_vp]),
     "nqb_tp_fused_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "nqb_nl_bin": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "nqb_nl_count": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nqb_nl_fill": (_i32, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nqb_sh_fwd": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp]),
     "nqb_sh_bwd": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "nqb_edge_embed_fwd": (

@@ -61,7 +61,7 @@ def runtime_lib_path() -> str:
 def ensure_runtime(force: bool = False) -> str:
     """Build (if stale) and return the path of libnqb.so."""
     out = runtime_lib_path()
-    cus = [os.path.join(CSRC, n) for n in ("nqb_runtime.cu", "nqb_mlp.cu", "nqb_gemm.cu", "nqb_gemm_t.cu")]
+    cus = [os.path.join(CSRC, n) for n in ("nqb_runtime.cu", "nqb_mlp.cu", "nqb_gemm.cu", "nqb_gemm_t.cu", "nqb_nl.cu")]
     srcs = cus + [os.path.join(INCLUDE, "nqb.h"), os.path.join(CSRC, "nqb_tc.cuh")]
     with _lock:
         if force or _newer(srcs, out):

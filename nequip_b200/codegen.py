@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 15
+CODEGEN_VERSION = 16
 
 
 # ---------------------------------------------------------------------------
@@ -174,13 +174,15 @@ class GenOptions:
     fwd_ring: bool = True  # forward v2: one CTA per node, weight rows streamed through a cp.async.bulk smem ring
     ring_stages: int = 4
     bwd_ring: bool = True  # backward v2 (same weight ring)
+    fused_prof: bool = False  # per-role stall counters in the fused radial-MLP + TP kernel (tools/bench_fused.py --prof)
     layout: str = "mul_ir"  # node-feature layout of x / out: "mul_ir" (the reference's, e3nn) or
     #                         "ir_mul" (channel-contiguous: every chunk is [2l+1, mul]; all node-feature
     #                         traffic becomes unit-stride 8-byte accesses; used between our own kernels)
 
     def tag(self) -> str:
         return (f"w{self.nwarp}_a{self.acc_cap}_b{self.acc_cap_bwd}_p{int(self.prefetch)}{int(self.idx_ahead)}"
-                f"_m{self.min_blocks_fwd}{self.min_blocks_bwd}_r{int(self.red_v2)}_{self.layout}_g{int(self.fwd_ring)}{self.ring_stages}{int(self.bwd_ring)}")
+                f"_m{self.min_blocks_fwd}{self.min_blocks_bwd}_r{int(self.red_v2)}_{self.layout}_g{int(self.fwd_ring)}{self.ring_stages}{int(self.bwd_ring)}"
+                + ("_fp" if self.fused_prof else ""))
 
 
 # ---------------------------------------------------------------------------
@@ -853,7 +855,7 @@ class TPGenerator:
             xrow = max(xrow, sum(n for (_o, n, _i) in sg))
         if xrow % 4 or sig.d_in % 4:
             return None
-        fixed = 2 * 2 * 64 * 128 * 4 + 1024  # h tiles (hi, lo) x 2 stages + barriers
+        fixed = 2 * 2 * 64 * 128 * 4 + 2 * 4 * 7 * 32 * 4 + 1024  # h tiles (hi, lo) x 2 stages, set hand-over, barriers
         stage = 8 * (xrow + sig.s_dim) * 4
         nxs = min(16, (227 * 1024 - 1024 - fixed) // stage)
         if nxs < 6:
@@ -939,8 +941,8 @@ class TPGenerator:
         em("static __device__ __forceinline__ int seg_count(int s) { return FT_SEG_CNT[s]; }")
         em("static __device__ __forceinline__ int seg_goff(int s, int k) { return FT_SEG_GOFF[s * 4 + k]; }")
         em("static __device__ __forceinline__ int seg_len(int s, int k) { return FT_SEG_LEN[s * 4 + k]; }")
-        em.block("static __device__ __forceinline__ void consume(int slice, int quad, int lane, const FusedFwdArgs& a, FtSmem& S, "
-                 "const float* xring, uint32_t tmem)")
+        em.block("static __device__ __forceinline__ void consume(int slice, int set, int quad, int lane, const FusedFwdArgs& a, "
+                 "FtSmem& S, const float* xring, uint32_t tmem)")
         em.block("switch (slice * 4 + quad)")
         wpp = mul // 32  # warps per path
         for si, grp in enumerate(slices):
@@ -948,8 +950,8 @@ class TPGenerator:
                 slot = q // wpp
                 if slot < len(grp):
                     p = grp[slot]
-                    em(f"case {si * 4 + q}: ft_consumer<FtPath{p.idx}, FtSpec>(a, S, xring, tmem, quad, lane, {(q % wpp) * 32} + lane); break;")
-        em("default: ft_consumer<FtNullPath, FtSpec>(a, S, xring, tmem, quad, lane, lane); break;")
+                    em(f"case {si * 4 + q}: ft_consumer<FtPath{p.idx}, FtSpec>(a, S, xring, tmem, set, quad, lane, {(q % wpp) * 32} + lane); break;")
+        em("default: ft_consumer<FtNullPath, FtSpec>(a, S, xring, tmem, set, quad, lane, lane); break;")
         em.end()
         em.end()
         em.end("};")
@@ -966,6 +968,8 @@ class TPGenerator:
         em(f"// options: {self.opts.tag()}  fwd_groups={len(self.fwd_groups)} bwd_groups={len(self.bwd_groups)}")
         em(f"// forward multiply-accumulates per (edge, channel): {sig.fma_count()}")
         em("#include <cuda_runtime.h>")
+        if self.opts.fused_prof:
+            em("#define FT_PROF 1")
         em('#include "nqb_tc.cuh"')
         em("namespace {")
         em(f"constexpr int NWARP = {self.opts.nwarp};")
@@ -1230,6 +1234,8 @@ class TPGenerator:
         else:
             em("*nslice = 0; *nxs = 0; *xrow = 0; return -1;")
         em.end()
+        if self.opts.fused_prof and self.has_fused:
+            em('extern "C" int nqb_spec_fused_prof(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ft_prof, sizeof(unsigned long long) * 160 * 32); }')
         em.block('extern "C" int nqb_spec_fused_fwd(const float* x, const float* y, const float* h, int64_t ldh, int K, '
                  "const float* wprep, const int64_t* row_ptr, const int64_t* src, int64_t N, int64_t E, float* out, "
                  "float* w_out, const int32_t* slice_cta0, int nctas, cudaStream_t st)")

@@ -19,8 +19,16 @@
 // columns), keep the node's output in registers and write each output element exactly once (deterministic, no
 // atomics, no zero fill).  Weights are never re-streamed: 128 KB per CTA once, instead of 1.8 MB per 128 edges.
 //
-// Roles (384 threads): warps 0-3 consumers (TMEM lane quadrant = warp), warps 4-7 producers (cp.async: h tile +
-// its tf32 low part; x[src] rows and Y rows of the node's edges into an 8-edge-stage ring), warp 8 MMA issue.
+// Roles (512 threads; a first version with one warp per role and quadrant was a set of single-warp latency chains,
+// 10-40 k cycles per tile -- profiles/r02_fused_v1.jsonl):
+//   warps 0-7   consumers: two sets (set = warp / 4) x TMEM lane quadrant (warp % 4); of every 8-edge stage set 0
+//               takes edges 0-3 and set 1 edges 4-7, two edge PAIRS each, branch-free (padded edges have weight
+//               exactly 0 and finite stale operands), so the loads and FFMA2 chains of the pairs interleave; at the
+//               end of a node set 1 hands its partial sums to set 0 through shared memory (fixed order: deterministic)
+//   warps 8-11  h producers: cp.async of the node's h rows (one tile ahead) + tf32 low part
+//   warp  12    MMA issue (one elected lane), TMEM allocation
+//   warp  13    x / Y stager: ONE cp.async.bulk per (edge, input chunk) -- an ir_mul chunk is contiguous -- with
+//               mbarrier complete_tx, and 4-byte cp.async for the Y pairs
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,7 +41,7 @@ constexpr int FT_TE = 64;                       // max edges per tile = MMA N
 constexpr int FT_KMAX = 128;                    // resident K (hidden width of the radial MLP)
 constexpr int FT_SUB = 8;                       // edges per x/Y ring stage
 constexpr int FT_TILE_FLOATS = FT_TE * FT_KMAX; // 32 KB
-constexpr int FT_THREADS = 384;
+constexpr int FT_THREADS = 512;
 constexpr int FT_MAXSEG = 4;                    // distinct input chunks a slice may stage per edge
 
 struct FusedFwdArgs {
@@ -103,10 +111,27 @@ __device__ __forceinline__ void ft_cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Per-role stall accounting (generated with GenOptions(fused_prof=True), tools/bench_fused.py --prof): cycles CTA 0's
+// lane 0 of each role spends in each mbarrier wait, and the role's total.
+#ifdef FT_PROF
+__device__ unsigned long long ft_prof[160 * 32];  // per CTA: 4 roles x {6 sections, total, tiles}
+#define FTP_DECL long long pw_[6] = {0, 0, 0, 0, 0, 0}; const long long pt0_ = clock64();
+#define FTP_WAIT(i, stmt) { const long long t_ = clock64(); stmt; pw_[i] += clock64() - t_; }
+#define FTP_END(base, ntiles) { if (blockIdx.x < 160 && (threadIdx.x & 31) == 0) { \
+    for (int i_ = 0; i_ < 6; ++i_) ft_prof[blockIdx.x * 32 + (base) + i_] = (unsigned long long)pw_[i_]; \
+    ft_prof[blockIdx.x * 32 + (base) + 6] = (unsigned long long)(clock64() - pt0_); \
+    ft_prof[blockIdx.x * 32 + (base) + 7] = (unsigned long long)(ntiles); } }
+#else
+#define FTP_DECL
+#define FTP_WAIT(i, stmt) { stmt; }
+#define FTP_END(base, ntiles) {}
+#endif
+
 // shared memory: fixed part; the x/Y ring (NXS stages of STAGE_FLOATS floats) follows it
 struct FtSmem {
   float hraw[2][FT_TILE_FLOATS];   // h tiles (the fp32 tile is the tf32 high operand: the tensor core truncates)
   float hlo[2][FT_TILE_FLOATS];    // their tf32 low parts
+  float comb[2][4][7][32];         // set 1 -> set 0 partial sums of a node: [slot][quadrant][component][lane]
   uint64_t a_full[2], a_done[2], acc_full[2], acc_empty[2], w_full;
   uint64_t x_full[16], x_empty[16];
   uint32_t tmem_base;
@@ -124,73 +149,97 @@ __device__ __forceinline__ int64_t ft_lower_bound(const int64_t* __restrict__ ro
   return lo;
 }
 
+// 32 lanes x 4 columns from each of four TMEM addresses, one wait
+__device__ __forceinline__ void ft_tmem_ld4x4(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%16];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [%17];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [%18];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%12, %13, %14, %15}, [%19];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(t0), "r"(t1), "r"(t2), "r"(t3)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ft_bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------
-// consumer: one warp = 32 channels of one path (TMEM lanes quad*32 .. +31)
+// consumer: one warp = 32 channels of one path (TMEM lanes quad*32 .. +31), half of the edges of every stage
 // PathT (generated): ACTIVE, N1/N2/N3 (= 2l+1), XS_OFF (float offset of the input chunk inside a staged edge row),
 // Y_OFF, W_OFF, MUL, and  fma(x[N1], y[N2], w, acc[N3]),  store(out_row, u, acc),  store_zero(out_row, u)
 // ---------------------------------------------------------------------------------------------------------
 template <class P, class Spec>
-__device__ __forceinline__ void ft_consumer(const FusedFwdArgs& a, FtSmem& S, const float* xring, uint32_t tmem, int quad,
-                                            int lane, int u) {
+__device__ __forceinline__ void ft_consumer(const FusedFwdArgs& a, FtSmem& S, const float* xring, uint32_t tmem, int set,
+                                            int quad, int lane, int u) {
   constexpr int NXS = Spec::NXS, XROW = Spec::XROW, SD = Spec::S;
   constexpr int STAGE_FLOATS = FT_SUB * (XROW + SD);
+  constexpr int NA = P::N3 > 0 ? P::N3 : 1;
   const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
   const int64_t n0 = S.n0, n1 = S.n1;
-  float2 acc[P::N3 > 0 ? P::N3 : 1];
+  float2 acc[NA];
 #pragma unroll
   for (int k = 0; k < P::N3; ++k) acc[k] = make_float2(0.f, 0.f);
-  uint32_t it = 0, xs = 0;
+  uint32_t it = 0, xs = 0, slot = 0;
+  FTP_DECL
   for (int64_t n = n0; n < n1; ++n) {
     const int64_t beg = a.row_ptr[n], end = a.row_ptr[n + 1];
     if (beg == end) {
-      if (P::ACTIVE) P::store_zero(a.out + n * Spec::D_OUT, u);
+      if (P::ACTIVE && set == 0) P::store_zero(a.out + n * Spec::D_OUT, u);
       continue;
     }
     for (int64_t t0 = beg; t0 < end; t0 += FT_TE, ++it) {
       const int cnt = (int)((end - t0 < FT_TE) ? (end - t0) : FT_TE);
       const uint32_t buf = it & 1;
-      mbar_wait(&S.acc_full[buf], (it >> 1) & 1);
+      FTP_WAIT(0, mbar_wait(&S.acc_full[buf], (it >> 1) & 1))
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < cnt; c0 += 16) {
-        float w[16];
+        // this set's weights of the two stages of the chunk: columns c0 + 4 set + {0..3} and c0 + 8 + 4 set + {0..3}
+        float w[8];
         {
-          float hh[16], xx[16];
-          ft_tmem_ld16x2(tlane + 256 + buf * 128 + c0, tlane + 256 + buf * 128 + 64 + c0, hh, xx);
+          float t[16];
+          const uint32_t b0 = tlane + 256 + buf * 128 + c0 + 4 * set;
+          FTP_WAIT(2, ft_tmem_ld4x4(b0, b0 + 64, b0 + 8, b0 + 8 + 64, t))
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = hh[j] + xx[j];
+          for (int j = 0; j < 4; ++j) { w[j] = t[j] + t[4 + j]; w[4 + j] = t[8 + j] + t[12 + j]; }
         }
         if (c0 + 16 >= cnt) {  // every needed column of this buffer has been read
           tc_fence_before();
           mbar_arrive(&S.acc_empty[buf]);
         }
         if (P::ACTIVE && a.w_out != nullptr) {
-          float* wo = a.w_out + (t0 + c0) * (int64_t)Spec::W + P::W_OFF + u;
+          float* wo = a.w_out + (t0 + c0 + 4 * set) * (int64_t)Spec::W + P::W_OFF + u;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < cnt) wo[(int64_t)j * Spec::W] = w[j];
+          for (int j = 0; j < 8; ++j) {
+            const int e = (j < 4) ? j : (j + 4);
+            if (c0 + 4 * set + e < cnt) wo[(int64_t)e * Spec::W] = w[j];
+          }
         }
 #pragma unroll
         for (int sb = 0; sb < 2; ++sb) {
           const int e0 = c0 + sb * FT_SUB;
           if (e0 < cnt) {
             const uint32_t st = xs % NXS;
-            mbar_wait(&S.x_full[st], (xs / NXS) & 1);
+            FTP_WAIT(1, mbar_wait(&S.x_full[st], (xs / NXS) & 1))
             if (P::ACTIVE) {
-              const float* xb = xring + (size_t)st * STAGE_FLOATS + P::XS_OFF + u;
-              const float2* yb = reinterpret_cast<const float2*>(xring + (size_t)st * STAGE_FLOATS + FT_SUB * XROW) + P::Y_OFF;
+              // edges e0 + 4 set + {0,1} and {2,3}: no bounds tests -- an edge beyond the node has weight 0
+              const float* xb = xring + (size_t)st * STAGE_FLOATS + (4 * set) * XROW + P::XS_OFF + u;
+              const float2* yb = reinterpret_cast<const float2*>(xring + (size_t)st * STAGE_FLOATS + FT_SUB * XROW) +
+                                 (2 * set) * SD + P::Y_OFF;
+              float2 xa[P::N1], ya[P::N2], xc[P::N1], yc[P::N2];
 #pragma unroll
-              for (int q = 0; q < FT_SUB / 2; ++q) {
-                if (e0 + 2 * q < cnt) {
-                  float2 xv[P::N1], yv[P::N2];
-#pragma unroll
-                  for (int i = 0; i < P::N1; ++i)
-                    xv[i] = make_float2(xb[(2 * q) * XROW + i * P::MUL], xb[(2 * q + 1) * XROW + i * P::MUL]);
-#pragma unroll
-                  for (int j = 0; j < P::N2; ++j) yv[j] = yb[q * SD + j];
-                  P::fma(xv, yv, make_float2(w[sb * FT_SUB + 2 * q], w[sb * FT_SUB + 2 * q + 1]), acc);
-                }
+              for (int i = 0; i < P::N1; ++i) {
+                xa[i] = make_float2(xb[i * P::MUL], xb[XROW + i * P::MUL]);
+                xc[i] = make_float2(xb[2 * XROW + i * P::MUL], xb[3 * XROW + i * P::MUL]);
               }
+#pragma unroll
+              for (int j = 0; j < P::N2; ++j) { ya[j] = yb[j]; yc[j] = yb[SD + j]; }
+              P::fma(xa, ya, make_float2(w[sb * 4], w[sb * 4 + 1]), acc);
+              P::fma(xc, yc, make_float2(w[sb * 4 + 2], w[sb * 4 + 3]), acc);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.x_empty[st]);
@@ -199,12 +248,22 @@ __device__ __forceinline__ void ft_consumer(const FusedFwdArgs& a, FtSmem& S, co
         }
       }
     }
-    if (P::ACTIVE) {
-      P::store(a.out + n * Spec::D_OUT, u, acc);
+    // node done: set 1 -> shared memory -> set 0 adds (always in this order) and writes the row
+    if (P::ACTIVE && set == 1) {
 #pragma unroll
-      for (int k = 0; k < P::N3; ++k) acc[k] = make_float2(0.f, 0.f);
+      for (int k = 0; k < P::N3; ++k) S.comb[slot][quad][k][lane] = acc[k].x + acc[k].y;
     }
+    ft_bar_consumers();
+    if (P::ACTIVE && set == 0) {
+#pragma unroll
+      for (int k = 0; k < P::N3; ++k) acc[k].x = (acc[k].x + acc[k].y) + S.comb[slot][quad][k][lane];
+      FTP_WAIT(3, P::store(a.out + n * Spec::D_OUT, u, acc))
+    }
+#pragma unroll
+    for (int k = 0; k < P::N3; ++k) acc[k] = make_float2(0.f, 0.f);
+    slot ^= 1;
   }
+  if (quad == 0 && set == 0) FTP_END(0, it)
 }
 
 struct FtNullPath {
@@ -215,8 +274,31 @@ struct FtNullPath {
   static __device__ __forceinline__ void store_zero(float*, int) {}
 };
 
+// tile walker shared by the roles: the node's edges in chunks of FT_TE
+struct FtTile { int64_t t0; int cnt; bool ok; };
+struct FtWalker {
+  const int64_t* row_ptr; int64_t n, n1, off;
+  __device__ FtWalker(const int64_t* rp, int64_t n0_, int64_t n1_) : row_ptr(rp), n(n0_), n1(n1_), off(0) {}
+  __device__ __forceinline__ FtTile next() {
+    FtTile t; t.ok = false; t.t0 = 0; t.cnt = 0;
+    while (n < n1) {
+      const int64_t beg = row_ptr[n], end = row_ptr[n + 1];
+      if (beg + off < end) {
+        t.t0 = beg + off;
+        t.cnt = (int)((end - t.t0 < FT_TE) ? (end - t.t0) : FT_TE);
+        t.ok = true;
+        off += FT_TE;
+        if (beg + off >= end) { ++n; off = 0; }
+        return t;
+      }
+      ++n; off = 0;
+    }
+    return t;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------
-// the kernel.  Spec (generated): MUL, S, D_IN, D_OUT, W, NSLICE, XROW, NXS, seg tables, consume(slice, quad, ...)
+// the kernel.  Spec (generated): MUL, S, D_IN, D_OUT, W, NSLICE, XROW, NXS, seg tables, consume(slice, set, quad, ...)
 // ---------------------------------------------------------------------------------------------------------
 template <class Spec>
 __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const FusedFwdArgs a) {
@@ -230,9 +312,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&S.a_full[s], 128); mbar_init(&S.a_done[s], 1);
-      mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 128);
+      mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 256);
     }
-    for (int s = 0; s < NXS; ++s) { mbar_init(&S.x_full[s], 128); mbar_init(&S.x_empty[s], 4); }
+    for (int s = 0; s < NXS; ++s) { mbar_init(&S.x_full[s], 33); mbar_init(&S.x_empty[s], 8); }
     mbar_init(&S.w_full, 128);
     fence_barrier_init();
     // which slice / node range
@@ -244,7 +326,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
     S.n0 = (j == 0) ? 0 : ft_lower_bound(a.row_ptr, a.N, t_lo);
     S.n1 = (j + 1 == ns) ? a.N : ft_lower_bound(a.row_ptr, a.N, t_hi);
   }
-  if (warp == 8) tmem_alloc(&S.tmem_base, 512);
+  // the x / Y ring starts out as zeros: slots of edges beyond a node's last edge are never written, their weights
+  // are exactly 0 and whatever (finite) operands a slot still holds then contribute nothing
+  for (int i = tid; i < NXS * STAGE_FLOATS / 4; i += FT_THREADS) reinterpret_cast<float4*>(xring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == 12) tmem_alloc(&S.tmem_base, 512);
+  fence_proxy_async();  // the zero fill is ordered before the bulk copies into the ring
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -254,12 +340,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
   const int ksteps = a.K / 8;
   // TMEM columns: [0,128) W hi, [128,256) W lo, per accumulator buffer b: [256 + 128 b, +64) hi*hi, [+64, +128) cross terms
 
-  if (warp < 4) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ================= consumers: upload the slice's weights, then the tensor product ====================
-    {
-      const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-      const float* wrow = a.wprep + ((int64_t)slice * 2 * 128 + warp * 32 + lane) * FT_KMAX;
+  if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // ================= consumers: set 0 uploads the slice's weights, then the tensor product =================
+    const int set = warp >> 2, quad = warp & 3;
+    if (set == 0) {
+      const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+      const float* wrow = a.wprep + ((int64_t)slice * 2 * 128 + quad * 32 + lane) * FT_KMAX;
 #pragma unroll 1
       for (int part = 0; part < 2; ++part) {
 #pragma unroll 1
@@ -277,24 +364,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
       tc_fence_before();
       mbar_arrive(&S.w_full);
     }
-    Spec::consume(slice, warp, lane, a, S, xring, tmem);
-  } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    // ================= producers ===========================================================================
-    const int pw = warp - 4, ptid = tid - 128;
+    Spec::consume(slice, set, quad, lane, a, S, xring, tmem);
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    // ================= h producers ============================================================================
+    const int pw = warp - 8;
     const int r8 = lane & 7, kq = lane >> 3;
     const int kgroups = ksteps * 2;  // 16-byte k-groups the MMAs read
-    // slice staging table: segment s copies `len` floats from x row offset `goff` to stage row offset `soff`
-    const int nseg = Spec::seg_count(slice);
-    int ppe = 0;  // 16-byte pieces per edge
-    for (int s = 0; s < nseg; ++s) ppe += Spec::seg_len(slice, s) / 4;
+    FTP_DECL
     auto issue_h = [&](uint32_t it, int64_t t0, int cnt) {
       float* dst = S.hraw[it & 1];
       const int nrg = ((cnt + 15) & ~15) / 8;  // 8-row groups the MMA reads (N rounded up to 16)
 #pragma unroll 1
       for (int kb = pw; kb * 4 < kgroups; kb += 4) {
         const int kg = kb * 4 + kq, k = kg * 4;
-#pragma unroll 1
+#pragma unroll 2
         for (int rg = 0; rg < nrg; ++rg) {
           const int m = rg * 8 + r8;
           const bool in = m < cnt;
@@ -309,7 +393,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
 #pragma unroll 1
       for (int kb = pw; kb * 4 < kgroups; kb += 4) {
         const int kg = kb * 4 + kq;
-#pragma unroll 2
+#pragma unroll 4
         for (int rg = 0; rg < nrg; ++rg) {
           const float4 t = *reinterpret_cast<const float4*>(raw + rg * (FT_KMAX / 4 * 32) + kg * 32 + r8 * 4);
           *reinterpret_cast<float4*>(lo + rg * (FT_KMAX / 4 * 32) + kg * 32 + r8 * 4) =
@@ -317,73 +401,31 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
         }
       }
     };
-    uint32_t xs = 0;
-    auto issue_x = [&](int64_t t0, int cnt) {
-      for (int e0 = 0; e0 < cnt; e0 += FT_SUB, ++xs) {
-        const uint32_t st = xs % NXS;
-        if (xs >= (uint32_t)NXS) mbar_wait(&S.x_empty[st], ((xs / NXS) - 1) & 1);
-        float* stage = xring + (size_t)st * STAGE_FLOATS;
-        const int ne = (cnt - e0 < FT_SUB) ? (cnt - e0) : FT_SUB;
-        const int nep = ne + (ne & 1);  // the odd partner of a last single edge is zero-filled
-        for (int p = ptid; p < nep * ppe; p += 128) {
-          const int e = p / ppe;
-          int k = p - e * ppe, s = 0, soff = 0;
-          while (s + 1 < nseg && k >= Spec::seg_len(slice, s) / 4) { k -= Spec::seg_len(slice, s) / 4; soff += Spec::seg_len(slice, s); ++s; }
-          const bool valid = e < ne;
-          const int64_t row = valid ? a.src[t0 + e0 + e] : 0;
-          cp_async16(stage + e * XROW + soff + k * 4, a.x + row * Spec::D_IN + Spec::seg_goff(slice, s) + k * 4, valid ? 16u : 0u);
-        }
-        float* ys = stage + FT_SUB * XROW;  // [pair][S][2]
-        for (int p = ptid; p < nep * SD; p += 128) {
-          const int e = p / SD, j = p - e * SD;
-          const bool valid = e < ne;
-          ft_cp_async4(ys + ((e >> 1) * SD + j) * 2 + (e & 1), a.y + (valid ? (t0 + e0 + e) * SD + j : 0), valid ? 4u : 0u);
-        }
-        ft_cp_async_arrive(&S.x_full[st]);
-      }
-    };
-    // tile walk with the h tile one tile ahead:  group(it) = { x of tile it - 2 ..., h of tile it }
-    struct Tile { int64_t t0; int cnt; bool ok; };
-    int64_t wn = n0, wt = 0;  // walker: node, offset inside the node
-    auto next_tile = [&]() {
-      Tile t; t.ok = false; t.t0 = 0; t.cnt = 0;
-      while (wn < n1) {
-        const int64_t beg = a.row_ptr[wn], end = a.row_ptr[wn + 1];
-        if (beg + wt < end) {
-          t.t0 = beg + wt;
-          t.cnt = (int)((end - t.t0 < FT_TE) ? (end - t.t0) : FT_TE);
-          t.ok = true;
-          wt += FT_TE;
-          if (beg + wt >= end) { ++wn; wt = 0; }
-          return t;
-        }
-        ++wn; wt = 0;
-      }
-      return t;
-    };
+    // h one tile ahead: group(it) = { h of tile it }
+    FtWalker wk(a.row_ptr, n0, n1);
     uint32_t it = 0;
-    Tile cur = next_tile();
+    FtTile cur = wk.next();
     if (cur.ok) issue_h(0, cur.t0, cur.cnt);
     cp_async_commit();
     while (cur.ok) {
-      const Tile nxt = next_tile();
+      const FtTile nxt = wk.next();
       if (nxt.ok) {
-        if (it + 1 >= 2) mbar_wait(&S.a_done[(it + 1) & 1], (((it + 1) >> 1) - 1) & 1);  // MMAs of tile it - 1 done
-        issue_h(it + 1, nxt.t0, nxt.cnt);
+        if (it + 1 >= 2) FTP_WAIT(0, mbar_wait(&S.a_done[(it + 1) & 1], (((it + 1) >> 1) - 1) & 1))  // MMAs of tile it - 1 done
+        FTP_WAIT(5, issue_h(it + 1, nxt.t0, nxt.cnt))
       }
       cp_async_commit();
-      cp_async_wait<1>();  // h of tile `it` (and every older copy) has landed
-      lo_pass(it, cur.cnt);
+      FTP_WAIT(2, cp_async_wait<1>())  // h of tile `it` has landed
+      FTP_WAIT(3, lo_pass(it, cur.cnt))
       fence_proxy_async();
       mbar_arrive(&S.a_full[it & 1]);
-      issue_x(cur.t0, cur.cnt);
       cur = nxt;
       ++it;
     }
     cp_async_wait<0>();
+    if (warp == 8) FTP_END(8, it)
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 12) {
       // ================= MMA issue ===========================================================================
       const bool leader = elect_one();
       constexpr uint32_t SBO = (FT_KMAX / 4) * 128, LBO = 128;
@@ -393,16 +435,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
       mbar_wait(&S.w_full, 0);
       tc_fence_after();
       uint32_t it = 0;
+      FTP_DECL
       for (int64_t n = n0; n < n1; ++n) {
         const int64_t beg = a.row_ptr[n], end = a.row_ptr[n + 1];
         for (int64_t t0 = beg; t0 < end; t0 += FT_TE, ++it) {
           const int cnt = (int)((end - t0 < FT_TE) ? (end - t0) : FT_TE);
           const uint32_t buf = it & 1, s = it & 1;
           const uint32_t idesc = make_idesc(128, (cnt + 15) & ~15);
-          if (it >= 2) { mbar_wait(&S.acc_empty[buf], ((it >> 1) - 1) & 1); tc_fence_after(); }
+          if (it >= 2) { FTP_WAIT(0, mbar_wait(&S.acc_empty[buf], ((it >> 1) - 1) & 1)) tc_fence_after(); }
           const uint64_t b_hi = dR0 + (uint64_t)(s * STAGE), b_lo = dL0 + (uint64_t)(s * STAGE);
           const uint32_t d_hh = tmem + 256 + buf * 128, d_x = d_hh + 64;
-          mbar_wait(&S.a_full[s], (it >> 1) & 1);
+          FTP_WAIT(1, mbar_wait(&S.a_full[s], (it >> 1) & 1))
           if (leader) {
             // one k-step = 8 tf32 = 8 TMEM columns of the weights, 2 core matrices (16 descriptor units) of the h rows
 #pragma unroll 4
@@ -417,11 +460,73 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
           __syncwarp();
         }
       }
+      FTP_END(16, it)
+    } else if (warp == 13) {
+      // ================= x / Y stager ========================================================================
+      // lanes 0-7 = the edges of a stage: one bulk copy per (edge, input chunk of the slice); all lanes: Y elements
+      const int nseg = Spec::seg_count(slice);
+      int goff[FT_MAXSEG], slen[FT_MAXSEG], soff[FT_MAXSEG], rowbytes = 0;
+#pragma unroll
+      for (int s = 0; s < FT_MAXSEG; ++s) {
+        goff[s] = (s < nseg) ? Spec::seg_goff(slice, s) : 0;
+        slen[s] = (s < nseg) ? Spec::seg_len(slice, s) : 0;
+        soff[s] = rowbytes / 4;
+        rowbytes += slen[s] * 4;
+      }
+      constexpr int YPL = (FT_SUB * SD + 31) / 32;  // Y elements per lane and stage
+      int ye[YPL], yj[YPL];
+#pragma unroll
+      for (int q = 0; q < YPL; ++q) { const int idx = lane + 32 * q; ye[q] = idx / SD; yj[q] = idx - ye[q] * SD; }
+      FtWalker wk(a.row_ptr, n0, n1);
+      FtTile cur = wk.next();
+      int64_t r0 = 0, r1 = 0, q0 = 0, q1 = 0;  // source rows of the tile's edges lane and 32 + lane (current / next tile)
+      if (cur.ok) {
+        r0 = (lane < cur.cnt) ? __ldg(a.src + cur.t0 + lane) : 0;
+        r1 = (32 + lane < cur.cnt) ? __ldg(a.src + cur.t0 + 32 + lane) : 0;
+      }
+      uint32_t xs = 0, it = 0;
+      FTP_DECL
+      while (cur.ok) {
+        const FtTile nxt = wk.next();
+        if (nxt.ok) {
+          q0 = (lane < nxt.cnt) ? __ldg(a.src + nxt.t0 + lane) : 0;
+          q1 = (32 + lane < nxt.cnt) ? __ldg(a.src + nxt.t0 + 32 + lane) : 0;
+        }
+#pragma unroll
+        for (int sb = 0; sb < FT_TE / FT_SUB; ++sb) {
+          const int e0 = sb * FT_SUB;
+          if (e0 < cur.cnt) {
+            const uint32_t st = xs % NXS;
+            if (xs >= (uint32_t)NXS) FTP_WAIT(1, mbar_wait(&S.x_empty[st], ((xs / NXS) - 1) & 1))
+            float* stage = xring + (size_t)st * STAGE_FLOATS;
+            const int ne = (cur.cnt - e0 < FT_SUB) ? (cur.cnt - e0) : FT_SUB;
+            const int64_t row = __shfl_sync(0xffffffffu, (sb < 4) ? r0 : r1, (e0 + (lane & 7)) & 31);
+            if (lane == 0) mbar_expect_tx(&S.x_full[st], (uint32_t)(ne * rowbytes));
+            if (lane < ne) {
+              const float* xrow = a.x + row * Spec::D_IN;
+#pragma unroll
+              for (int s = 0; s < FT_MAXSEG; ++s)
+                if (s < nseg) bulk_g2s(stage + lane * XROW + soff[s], xrow + goff[s], (uint32_t)(slen[s] * 4), &S.x_full[st]);
+            }
+            float* ys = stage + FT_SUB * XROW;  // [pair][S][2]
+#pragma unroll
+            for (int q = 0; q < YPL; ++q)
+              if (ye[q] < ne) ft_cp_async4(ys + ((ye[q] >> 1) * SD + yj[q]) * 2 + (ye[q] & 1), a.y + (cur.t0 + e0 + ye[q]) * SD + yj[q], 4u);
+            ft_cp_async_arrive(&S.x_full[st]);
+            ++xs;
+          }
+        }
+        r0 = q0; r1 = q1;
+        cur = nxt;
+        ++it;
+      }
+      cp_async_wait<0>();
+      FTP_END(24, it)
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
 template <class Spec>

@@ -43,6 +43,10 @@ ATOM_TYPE_KEY = "atom_types"
 TOTAL_ENERGY_KEY = "total_energy"
 PER_ATOM_ENERGY_KEY = "atomic_energy"
 FORCE_KEY = "forces"
+STRESS_KEY = "stress"
+VIRIAL_KEY = "virial"
+EDGE_VECTORS_KEY = "edge_vectors"
+EDGE_FORCE_KEY = "edge_forces"
 BATCH_KEY = "batch"
 BATCH_PTR_KEY = "ptr"
 NUM_NODES_KEY = "num_atoms"
@@ -548,9 +552,16 @@ class NequIPEnergyModel(torch.nn.Module):
         shift, cell = data.get(EDGE_CELL_SHIFT_KEY), data.get(CELL_KEY)
         if cell is None:
             shift = None
-        _vec, edge_attrs, edge_embedding = ops.edge_embed(
-            pos, edge_index, shift, cell, lmax=self.l_max, num_bessel=self.num_bessels, r_max=self.r_max,
-            poly_p=self.poly_p, prefactor=(2 * math.pi) / (self.r_max * self.r_max), out_dtype=self.model_dtype)
+        pre = (2 * math.pi) / (self.r_max * self.r_max)
+        if EDGE_VECTORS_KEY in data:
+            # the caller (LAMMPS ML-IAP) supplies the edge vectors: with_edge_vectors_ keeps them (nn/utils.py:68-118)
+            edge_attrs, edge_embedding = ops.edge_embed_from_vectors(
+                data[EDGE_VECTORS_KEY], lmax=self.l_max, num_bessel=self.num_bessels, r_max=self.r_max,
+                poly_p=self.poly_p, prefactor=pre, out_dtype=self.model_dtype)
+        else:
+            _vec, edge_attrs, edge_embedding = ops.edge_embed(
+                pos, edge_index, shift, cell, lmax=self.l_max, num_bessel=self.num_bessels, r_max=self.r_max,
+                poly_p=self.poly_p, prefactor=pre, out_dtype=self.model_dtype, edge_grad_sink=data.get("_edge_grad_sink"))
         for layer in self.layers:
             x = layer(x, node_attrs, edge_attrs, edge_embedding, edge_index, types, self.type_embed.weight)
         e_atom = self.readout(x).to(torch.float64)
@@ -585,17 +596,51 @@ class NequIPEnergyModel(torch.nn.Module):
             e_atom = e_atom + self.shifts[t_own]
         return e_atom
 
-    def forward(self, data: Dict[str, torch.Tensor], compute_forces: bool = True) -> Dict[str, torch.Tensor]:
+    def forward(self, data: Dict[str, torch.Tensor], compute_forces: bool = True,
+                compute_stress: bool = False) -> Dict[str, torch.Tensor]:
+        """``ForceStressOutput.forward`` (nequip/nn/grad_output.py:107-298):
+
+        * positions given: ``forces = -dE/dpos``; with ``compute_stress`` (needs ``cell``) also
+          ``stress = (1/|det cell|) dE/d(eps)`` and ``virial = -dE/d(eps)`` ([1,3,3]) for the symmetric strain
+          ``eps`` applied to positions and cell.  The cell/strain gradient is not taken through a displaced
+          copy of the inputs: every edge vector transforms as ``r -> r (1 + eps)``, so
+          ``dE/d(eps) = sym( sum_e r_e (x) dE/dr_e )`` and the per-edge gradients are a by-product of the
+          edge-embedding backward kernel;
+        * ``edge_vectors`` given (LAMMPS ML-IAP): ``edge_forces = dE/d(edge_vectors)``, no sign flip (:270-296).
+        """
         data = dict(data)
         if not compute_forces:
             return self.energy(data)
+        if EDGE_VECTORS_KEY in data:
+            with torch.enable_grad():
+                vec = data[EDGE_VECTORS_KEY].detach().double().requires_grad_(True)
+                data[EDGE_VECTORS_KEY] = vec
+                data = self.energy(data)
+                (g,) = torch.autograd.grad([data[TOTAL_ENERGY_KEY].sum()], [vec])
+            data[EDGE_FORCE_KEY] = g
+            data[EDGE_VECTORS_KEY] = vec.detach()
+            data[TOTAL_ENERGY_KEY] = data[TOTAL_ENERGY_KEY].detach()
+            data[PER_ATOM_ENERGY_KEY] = data[PER_ATOM_ENERGY_KEY].detach()
+            return data
+        if compute_stress and data.get(CELL_KEY) is None:
+            raise ValueError("compute_stress needs a cell")
         pos = data[POSITIONS_KEY]
+        sink = {} if compute_stress else None
         with torch.enable_grad():
             pos = pos.detach().requires_grad_(True)
             data[POSITIONS_KEY] = pos
+            if sink is not None:
+                data["_edge_grad_sink"] = sink
             data = self.energy(data)
             (g,) = torch.autograd.grad([data[TOTAL_ENERGY_KEY].sum()], [pos])
+        data.pop("_edge_grad_sink", None)
         data[FORCE_KEY] = torch.neg(g)
+        if sink is not None:
+            v = torch.einsum("ea,eb->ab", sink["edge_vectors"], sink["edge_vector_grad"])
+            v = 0.5 * (v + v.t())
+            vol = torch.linalg.det(data[CELL_KEY].double().view(3, 3)).abs()
+            data[STRESS_KEY] = (v / vol).view(1, 3, 3)
+            data[VIRIAL_KEY] = torch.neg(v).view(1, 3, 3)
         data[POSITIONS_KEY] = pos.detach()
         data[TOTAL_ENERGY_KEY] = data[TOTAL_ENERGY_KEY].detach()
         data[PER_ATOM_ENERGY_KEY] = data[PER_ATOM_ENERGY_KEY].detach()

@@ -388,7 +388,7 @@ def spherical_harmonics(vec: torch.Tensor, lmax: int, out_dtype=torch.float32) -
 
 class _EdgeEmbedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, edge_index, shift, cell, lmax, num_bessel, r_max, poly_p, prefactor, out_dtype):
+    def forward(ctx, pos, edge_index, shift, cell, lmax, num_bessel, r_max, poly_p, prefactor, out_dtype, sink=None):
         L = _capi.lib()
         N, E = pos.shape[0], edge_index.shape[1]
         dev = pos.device
@@ -401,6 +401,7 @@ class _EdgeEmbedFn(torch.autograd.Function):
             "nqb_edge_embed_fwd",
         )
         ctx.args = (lmax, num_bessel, r_max, poly_p, prefactor, out_dtype, N)
+        ctx.sink = sink
         ctx.save_for_backward(vec, edge_index)
         ctx.mark_non_differentiable(vec)
         return vec, y, emb
@@ -415,20 +416,77 @@ class _EdgeEmbedFn(torch.autograd.Function):
         gpos = torch.zeros((N, 3), dtype=torch.float64, device=vec.device)
         gy = None if gy is None else gy.to(out_dtype).contiguous()
         gemb = None if gemb is None else gemb.to(out_dtype).contiguous()
+        # the per-edge gradient dE/d(edge vector) is what the virial is made of (sum_e r_e (x) g_e): keep it
+        # when the caller asked for it
+        gvec = torch.empty_like(vec) if ctx.sink is not None else None
         _capi.check(
             L.nqb_edge_embed_bwd(lmax, num_bessel, r_max, poly_p, prefactor, _ptr(vec), _ptr(edge_index), N, E,
-                                 _DT[out_dtype], _ptr(gy), _ptr(gemb), _ptr(gpos), 0, _stream()),
+                                 _DT[out_dtype], _ptr(gy), _ptr(gemb), _ptr(gpos), _ptr(gvec), _stream()),
             "nqb_edge_embed_bwd",
         )
-        return gpos, None, None, None, None, None, None, None, None, None
+        if ctx.sink is not None:
+            ctx.sink["edge_vectors"], ctx.sink["edge_vector_grad"] = vec, gvec
+        return gpos, None, None, None, None, None, None, None, None, None, None
+
+
+class _EdgeEmbedVecFn(torch.autograd.Function):
+    """Harmonics + radial embedding of GIVEN edge vectors (the ML-IAP branch: LAMMPS hands over the vectors,
+    nequip/nn/grad_output.py:270-296); backward = dE/d(edge vectors)."""
+
+    @staticmethod
+    def forward(ctx, vec, lmax, num_bessel, r_max, poly_p, prefactor, out_dtype):
+        L = _capi.lib()
+        E = vec.shape[0]
+        dev = vec.device
+        # the fused kernel computes pos[src] - pos[dst]: atoms 0..E-1 are the vectors, atom E is the origin
+        pos = torch.cat([vec, torch.zeros((1, 3), dtype=torch.float64, device=dev)], 0)
+        ar = torch.arange(E, dtype=torch.int64, device=dev)
+        edge_index = torch.stack([torch.full_like(ar, E), ar]).contiguous()
+        vec_out = torch.empty((E, 3), dtype=torch.float64, device=dev)
+        y = torch.empty((E, (lmax + 1) ** 2), dtype=out_dtype, device=dev)
+        emb = torch.empty((E, num_bessel), dtype=out_dtype, device=dev)
+        _capi.check(
+            L.nqb_edge_embed_fwd(lmax, num_bessel, r_max, poly_p, prefactor, _ptr(pos), _ptr(edge_index), 0, 0, E + 1, E,
+                                 _DT[out_dtype], _ptr(vec_out), _ptr(y), _ptr(emb), _stream()),
+            "nqb_edge_embed_fwd",
+        )
+        ctx.args = (lmax, num_bessel, r_max, poly_p, prefactor, out_dtype)
+        ctx.save_for_backward(vec_out, edge_index)
+        return y, emb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy, gemb):
+        vec, edge_index = ctx.saved_tensors
+        lmax, num_bessel, r_max, poly_p, prefactor, out_dtype = ctx.args
+        E = vec.shape[0]
+        gvec = torch.empty_like(vec)
+        gy = None if gy is None else gy.to(out_dtype).contiguous()
+        gemb = None if gemb is None else gemb.to(out_dtype).contiguous()
+        _capi.check(
+            _capi.lib().nqb_edge_embed_bwd(lmax, num_bessel, r_max, poly_p, prefactor, _ptr(vec), _ptr(edge_index), E + 1, E,
+                                           _DT[out_dtype], _ptr(gy), _ptr(gemb), 0, _ptr(gvec), _stream()),
+            "nqb_edge_embed_bwd",
+        )
+        return gvec, None, None, None, None, None, None
+
+
+def edge_embed_from_vectors(vec, *, lmax: int, num_bessel: int = 8, r_max: float, poly_p: float = 6.0,
+                            prefactor: float = 1.0, out_dtype=torch.float32):
+    """``(edge_attrs [E,(lmax+1)^2], edge_embedding [E,num_bessel])`` of given ``[E,3]`` edge vectors,
+    differentiable w.r.t. the vectors."""
+    _require_cuda(vec)
+    return _EdgeEmbedVecFn.apply(vec.double().contiguous(), int(lmax), int(num_bessel), float(r_max), float(poly_p),
+                                 float(prefactor), out_dtype)
 
 
 def edge_embed(pos, edge_index, shift=None, cell=None, *, lmax: int, num_bessel: int = 8, r_max: float,
-               poly_p: float = 6.0, prefactor: float = 1.0, out_dtype=torch.float32):
+               poly_p: float = 6.0, prefactor: float = 1.0, out_dtype=torch.float32, edge_grad_sink=None):
     """Edge vectors, harmonics and Bessel x cutoff embedding in one kernel.
 
     Returns ``(edge_vectors [E,3] f64, edge_attrs [E,(lmax+1)^2], edge_embedding [E,num_bessel])``.
-    Differentiable w.r.t. ``pos`` (forces); the cell gradient (stress) is not provided here."""
+    Differentiable w.r.t. ``pos`` (forces).  ``edge_grad_sink`` (a dict): the backward pass also stores the
+    edge vectors and dE/d(edge vector) in it, from which the virial / cell gradient follows."""
     _require_cuda(pos, edge_index)
     pos = pos.double().contiguous()
     edge_index = edge_index.long().contiguous()
@@ -438,7 +496,7 @@ def edge_embed(pos, edge_index, shift=None, cell=None, *, lmax: int, num_bessel:
         shift = shift.double().contiguous()
         cell = cell.double().reshape(3, 3).contiguous()
     return _EdgeEmbedFn.apply(pos, edge_index, shift, cell, int(lmax), int(num_bessel), float(r_max),
-                              float(poly_p), float(prefactor), out_dtype)
+                              float(poly_p), float(prefactor), out_dtype, edge_grad_sink)
 
 
 # ---------------------------------------------------------------------------------------
@@ -656,3 +714,81 @@ class GemmT:
         _capi.check(_capi.lib().nqb_gemm_t_run(_ptr(self.prepared), self.K, self.N, _ptr(a), a.stride(0), _ptr(c),
                                                c.stride(0), M, _stream()), "nqb_gemm_t_run")
         return c
+
+
+# ---------------------------------------------------------------------------------------
+# neighbour list on the device -- nqb_nl_bin / nqb_nl_count / nqb_nl_fill   
+# ---------------------------------------------------------------------------------------
+def neighbor_list(pos: torch.Tensor, cell=None, pbc=True, r_max: float = 5.0, transpose_perm: bool = False):
+    """Full neighbour list within ``r_max`` built on the GPU (cell list), in the layout the convolution wants.
+
+    ``pos`` [N,3] float64 CUDA; ``cell`` [3,3] (rows = lattice vectors; host or device) or None; ``pbc`` bool or 3
+    bools.  Returns a dict with ``edge_index`` [2,E] int64 (row 0 = centre / scatter destination, row 1 =
+    neighbour), ``edge_cell_shift`` [E,3] float64 (edge vector = pos[j] - pos[i] + shift @ cell), ``row_ptr``
+    [N+1] int64 (destination CSR: edges are sorted by (centre, neighbour)) and, on request,
+    ``edge_transpose_perm`` [E] (argsort by (neighbour, centre), nequip/data/transforms/neighborlist.py:150-155).
+    Same contract as the reference's host backends (nequip/data/_nl.py:60-152): both directions, no self edge in
+    the home image.  One host synchronisation (the edge count)."""
+    import numpy as np
+
+    _require_cuda(pos)
+    L = _capi.lib()
+    pos = pos.detach().double().contiguous()
+    N = pos.shape[0]
+    dev = pos.device
+    if isinstance(pbc, bool):
+        pbc = (pbc,) * 3
+    pbc = [bool(b) for b in (pbc.tolist() if torch.is_tensor(pbc) else pbc)]
+    if cell is None:
+        if any(pbc):
+            raise ValueError("Periodic boundary conditions requested but no cell was provided.")
+        cell_np = np.eye(3)
+    else:
+        cell_np = (cell.detach().cpu().double().reshape(3, 3).numpy() if torch.is_tensor(cell) else np.asarray(cell, dtype=np.float64).reshape(3, 3)).copy()
+    inv_np = np.linalg.inv(cell_np)
+    # distance between opposite faces along each lattice direction = 1 / |column d of the inverse|
+    perp = 1.0 / np.linalg.norm(inv_np, axis=0)
+    lo = np.zeros(3)
+    width = np.ones(3)
+    if not all(pbc) and N > 0:
+        frac = pos @ torch.as_tensor(inv_np, device=dev)
+        fmin, fmax = frac.min(0).values.cpu().numpy(), frac.max(0).values.cpu().numpy()
+        for d in range(3):
+            if not pbc[d]:
+                lo[d], width[d] = fmin[d], max(fmax[d] - fmin[d], 1e-9) * (1 + 1e-9)
+    nb, sr = [1, 1, 1], [1, 1, 1]
+    cap = max(1, int(round((4 * max(N, 1)) ** (1.0 / 3.0))))
+    for d in range(3):
+        extent = perp[d] * (1.0 if pbc[d] else width[d])
+        nb[d] = int(min(cap, max(1, np.floor(extent / r_max))))
+        sr[d] = int(np.ceil(r_max / (extent / nb[d]) - 1e-12)) if pbc[d] else 1
+        sr[d] = max(sr[d], 1)
+    I3 = C.c_int * 3
+    D9, D3 = C.c_double * 9, C.c_double * 3
+    cell_c, inv_c = D9(*cell_np.reshape(-1)), D9(*inv_np.reshape(-1))
+    pbc_c, nb_c, sr_c = I3(*[int(b) for b in pbc]), I3(*nb), I3(*sr)
+    lo_c, wd_c = D3(*lo), D3(*width)
+    st = _stream()
+    wpos = torch.empty((N, 3), dtype=torch.float64, device=dev)
+    base = torch.empty((N, 3), dtype=torch.int32, device=dev)
+    cidx = torch.empty((N, 3), dtype=torch.int32, device=dev)
+    binid = torch.empty((N,), dtype=torch.int64, device=dev)
+    _capi.check(L.nqb_nl_bin(_ptr(pos), N, cell_c, inv_c, pbc_c, nb_c, sr_c, lo_c, wd_c, float(r_max), _ptr(wpos), _ptr(base),
+                             _ptr(binid), _ptr(cidx), st), "nqb_nl_bin")
+    nbins = nb[0] * nb[1] * nb[2]
+    sorted_bin, order = torch.sort(binid, stable=True)
+    bin_start = torch.searchsorted(sorted_bin, torch.arange(nbins + 1, device=dev, dtype=torch.int64)).contiguous()
+    counts = torch.zeros((N,), dtype=torch.int64, device=dev)
+    _capi.check(L.nqb_nl_count(N, cell_c, inv_c, pbc_c, nb_c, sr_c, float(r_max), _ptr(wpos), _ptr(cidx), _ptr(order),
+                               _ptr(bin_start), _ptr(counts), st), "nqb_nl_count")
+    row_ptr = torch.zeros((N + 1,), dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=row_ptr[1:])
+    E = int(row_ptr[-1].item())
+    edge_index = torch.empty((2, E), dtype=torch.int64, device=dev)
+    shifts = torch.empty((E, 3), dtype=torch.float64, device=dev)
+    _capi.check(L.nqb_nl_fill(N, E, cell_c, inv_c, pbc_c, nb_c, sr_c, float(r_max), _ptr(wpos), _ptr(cidx), _ptr(base),
+                              _ptr(order), _ptr(bin_start), _ptr(row_ptr), _ptr(edge_index), _ptr(shifts), st), "nqb_nl_fill")
+    out = {"edge_index": edge_index, "edge_cell_shift": shifts, "row_ptr": row_ptr}
+    if transpose_perm:
+        out["edge_transpose_perm"] = torch.argsort(edge_index[1] * N + edge_index[0], stable=True)
+    return out

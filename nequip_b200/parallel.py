@@ -61,6 +61,47 @@ def slab_owner(pos: torch.Tensor, world: int, axis: int = 0) -> torch.Tensor:
     return owner
 
 
+def brick_grid(world: int, lengths, halo: float = 5.0) -> tuple:
+    """Factorisation (gx, gy, gz) of ``world`` whose bricks of a box with edge ``lengths`` have the smallest
+    halo volume (= fewest ghost atoms) for a halo of thickness ``halo``: elongated boxes get slabs, cubic
+    boxes 3-D bricks."""
+    best, best_v = (world, 1, 1), None
+    for gx in range(1, world + 1):
+        if world % gx:
+            continue
+        for gy in range(1, world // gx + 1):
+            if (world // gx) % gy:
+                continue
+            gz = world // gx // gy
+            dims = [lengths[0] / gx, lengths[1] / gy, lengths[2] / gz]
+            # a direction that is split (or periodic with one brick thinner than the box) grows by the halo on both sides
+            grown = [min(L, d + 2 * halo) if g > 1 else d for d, g, L in zip(dims, (gx, gy, gz), lengths)]
+            vol = grown[0] * grown[1] * grown[2] - dims[0] * dims[1] * dims[2]
+            if best_v is None or vol < best_v - 1e-9:
+                best, best_v = (gx, gy, gz), vol
+    return best
+
+
+def brick_owner(pos: torch.Tensor, grid) -> torch.Tensor:
+    """Owner rank of every atom for a ``grid = (gx, gy, gz)`` brick decomposition with equal atom counts:
+    equal-count slabs along x, each cut into equal-count columns along y, each cut along z
+    (rank = (ix * gy + iy) * gz + iz).  ``grid = (world, 1, 1)`` reproduces ``slab_owner``."""
+    N = pos.shape[0]
+    owner = torch.zeros(N, dtype=torch.long)
+
+    def split(ids: torch.Tensor, axis: int, parts: int):
+        order = ids[torch.argsort(pos[ids, axis], stable=True)]
+        n = order.numel()
+        return [order[(n * r) // parts: (n * (r + 1)) // parts] for r in range(parts)]
+
+    gx, gy, gz = (int(g) for g in grid)
+    for ix, sx in enumerate(split(torch.arange(N), 0, gx)):
+        for iy, sy in enumerate(split(sx, 1, gy)):
+            for iz, sz in enumerate(split(sy, 2, gz)):
+                owner[sz] = (ix * gy + iy) * gz + iz
+    return owner
+
+
 def make_plans(edge_index: torch.Tensor, owner: torch.Tensor, world: int) -> List[ShardPlan]:
     """All ranks' plans from the global edge list (host-side preprocessing, like the neighbour list).
     ``edge_index[0]`` = destination/centre, ``edge_index[1]`` = source/neighbour."""
@@ -124,10 +165,14 @@ class _HaloExchangeFn(torch.autograd.Function):
     def forward(ctx, x_own, send_idx, send_splits, recv_splits, group):
         ctx.send_idx, ctx.send_splits, ctx.recv_splits, ctx.group = send_idx, send_splits, recv_splits, group
         ctx.n_own = x_own.shape[0]
-        send = x_own.index_select(0, send_idx).contiguous()
-        recv = x_own.new_empty((sum(recv_splits),) + tuple(x_own.shape[1:]))
-        dist.all_to_all_single(recv, send, output_split_sizes=recv_splits, input_split_sizes=send_splits, group=group)
-        return torch.cat([x_own, recv], dim=0)
+        send = x_own.index_select(0, send_idx)
+        # owned rows and received ghost rows share ONE buffer: the collective writes its tail in place
+        # (no torch.cat copy of the whole feature matrix)
+        full = x_own.new_empty((ctx.n_own + sum(recv_splits),) + tuple(x_own.shape[1:]))
+        full[: ctx.n_own].copy_(x_own)
+        dist.all_to_all_single(full[ctx.n_own:], send, output_split_sizes=recv_splits, input_split_sizes=send_splits,
+                               group=group)
+        return full
 
     @staticmethod
     def backward(ctx, g_full):
@@ -151,13 +196,33 @@ class HaloExchange:
         return _HaloExchangeFn.apply(x_own, self.send_idx, self.plan.send_splits, self.plan.recv_splits, self.group)
 
 
+def owner_reduce(g_local: torch.Tensor, plan: ShardPlan, halo: "HaloExchange") -> torch.Tensor:
+    """Per-atom quantity over owned + ghost atoms -> owned atoms: the ghost rows travel back to their owners
+    (transposed halo exchange) and are added there.  ``[n_own + n_ghost, C] -> [n_own, C]``."""
+    g_own = g_local[: plan.n_own].clone()
+    if plan.world > 1:
+        back = g_local.new_empty((sum(plan.send_splits),) + tuple(g_local.shape[1:]))
+        dist.all_to_all_single(back, g_local[plan.n_own:].contiguous(), output_split_sizes=plan.send_splits,
+                               input_split_sizes=plan.recv_splits, group=halo.group)
+        g_own.index_add_(0, halo.send_idx, back)
+    return g_own
+
+
 def sharded_energy_forces(model, local: Dict[str, torch.Tensor], plan: ShardPlan, halo: HaloExchange,
-                          reduce_forces: bool = True):
+                          reduce_forces=True):
     """Energy + forces of one frame sharded over ``plan.world`` ranks.
 
     ``model`` is a ``NequIPEnergyModel``; ``local`` the rank's ``shard_data`` on its device.
-    Returns (total_energy [1] f64 -- identical on all ranks, forces [N_global, 3] f64 or the
-    local gradient when ``reduce_forces`` is False)."""
+    Returns ``(total_energy [1] f64 -- identical on all ranks, forces)`` where ``forces`` depends on
+    ``reduce_forces``:
+
+    * ``"owner"`` -- ``[n_own, 3]``: the forces of the atoms this rank owns.  The gradient that the local
+      energy has w.r.t. the positions of GHOST atoms is sent back to their owners with the transposed halo
+      exchange (``[n_ghost, 3]`` doubles per rank -- what LAMMPS' reverse communication does,
+      nequip/integrations/lammps_mliap/lmp_mliap_wrapper.py:202-219), so the cost per rank is O(N / P);
+    * ``True`` / ``"global"`` -- ``[N_global, 3]`` on every rank (dense all-reduce; for tests and small frames);
+    * ``False`` -- the raw local gradient ``-dE_local/dpos`` over owned + ghost atoms.
+    """
     pos = local["pos"].detach().requires_grad_(True)
     d = dict(local)
     d["pos"] = pos
@@ -168,8 +233,10 @@ def sharded_energy_forces(model, local: Dict[str, torch.Tensor], plan: ShardPlan
     e = e_loc.detach().reshape(1).clone()
     if plan.world > 1:
         dist.all_reduce(e, group=halo.group)
-    if not reduce_forces:
+    if reduce_forces is False:
         return e, -g
+    if reduce_forces == "owner":
+        return e, -owner_reduce(g, plan, halo)
     f = torch.zeros((plan.num_global, 3), dtype=g.dtype, device=g.device)
     f.index_add_(0, plan.local_ids.to(g.device), -g)
     if plan.world > 1:

@@ -163,7 +163,9 @@ def mlp(x, weights, alphas):
 
 # ------------------------------------------------------------------ the model
 def energy(sd: Dict[str, torch.Tensor], cfg: dict, data: dict, model_dtype=torch.float32, tp_chunk: int = 0):
-    """Total energy [1,1] f64 and per-atom energies from ``state_dict`` sd of NequIPEnergyModel."""
+    """Total energy [1,1] f64 and per-atom energies from ``state_dict`` sd of NequIPEnergyModel.
+    With ``data["edge_vectors"]`` given the edge geometry is taken from it (the ML-IAP branch,
+    nequip/nn/utils.py:68-118 ``with_edge_vectors_`` keeps vectors that are already present)."""
     sd = {k: v.detach().cpu() for k, v in sd.items()}
     pos, edge_index, types = data["pos"], data["edge_index"], data["atom_types"].view(-1)
     cell, shift = data.get("cell"), data.get("edge_cell_shift")
@@ -171,8 +173,14 @@ def energy(sd: Dict[str, torch.Tensor], cfg: dict, data: dict, model_dtype=torch
         shift = None
     l_max, nf = cfg["l_max"], cfg["num_features"]
     sh_ir = I.spherical_harmonics(l_max)
-    _, y, emb = edge_embed(pos, edge_index, cell, shift, l_max, cfg["num_bessels"], cfg["r_max"],
-                           float(cfg["polynomial_cutoff_p"]), model_dtype)
+    if "edge_vectors" in data:
+        vec = data["edge_vectors"]
+        r = vec.square().sum(1, keepdim=True).sqrt()
+        y = osh.spherical_harmonics(l_max, vec, normalize=True).to(model_dtype)
+        emb = radial_embedding(r, cfg["r_max"], cfg["num_bessels"], float(cfg["polynomial_cutoff_p"]), model_dtype)
+    else:
+        _, y, emb = edge_embed(pos, edge_index, cell, shift, l_max, cfg["num_bessels"], cfg["r_max"],
+                               float(cfg["polynomial_cutoff_p"]), model_dtype)
     node_attrs = sd["type_embed.weight"].to(model_dtype)[types]
     x = node_attrs
     prev = [(nf, (0, 1))]
@@ -222,3 +230,30 @@ def energy_and_forces(sd, cfg, data, model_dtype=torch.float32, tp_chunk: int = 
     e_tot, e_atom = energy(sd, cfg, data, model_dtype, tp_chunk)
     (g,) = torch.autograd.grad([e_tot.sum()], [pos])
     return e_tot.detach(), e_atom.detach(), -g
+
+
+def energy_forces_stress(sd, cfg, data, model_dtype=torch.float32, tp_chunk: int = 0):
+    """ForceStressOutput (nequip/nn/grad_output.py:162-268): symmetric infinitesimal displacement applied to
+    positions and cell, forces = -dE/dpos, virial_raw = dE/d(displacement), stress = virial_raw / |det cell|,
+    virial = -virial_raw.  Returns (E, forces, stress [1,3,3], virial [1,3,3])."""
+    data = dict(data)
+    pos = data["pos"].detach().clone().requires_grad_(True)
+    disp = torch.zeros(3, 3, dtype=pos.dtype, requires_grad=True)
+    sym = 0.5 * (disp + disp.t())
+    data["pos"] = pos + torch.sum(pos.view(-1, 3, 1) * sym, 1)
+    cell = data["cell"].view(3, 3)
+    data["cell"] = cell + torch.sum(cell.view(3, 3, 1) * sym, 1)
+    e_tot, _ = energy(sd, cfg, data, model_dtype, tp_chunk)
+    g, v = torch.autograd.grad([e_tot.sum()], [pos, disp])
+    vol = torch.linalg.det(cell).abs()
+    return e_tot.detach(), -g, (v / vol).view(1, 3, 3), (-v).view(1, 3, 3)
+
+
+def edge_forces(sd, cfg, data, model_dtype=torch.float32):
+    """The ML-IAP branch of ForceStressOutput (grad_output.py:270-296): dE/d(edge_vectors), no sign flip."""
+    data = dict(data)
+    vec = data["edge_vectors"].detach().clone().requires_grad_(True)
+    data["edge_vectors"] = vec
+    e_tot, _ = energy(sd, cfg, data, model_dtype)
+    (g,) = torch.autograd.grad([e_tot.sum()], [vec])
+    return e_tot.detach(), g

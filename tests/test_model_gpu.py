@@ -140,3 +140,54 @@ def test_fused_gate_matches_torch_gate(layout, dtype, tol):
     (gx,) = torch.autograd.grad(out, xc, go.to("cuda", dtype))
     torch.testing.assert_close(out.detach().cpu().double(), ref.detach(), rtol=tol, atol=tol * 10)
     torch.testing.assert_close(gx.cpu().double(), gx_ref, rtol=tol * 5, atol=tol * 50)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-5)])
+def test_stress_and_virial_match_oracle(dtype, tol):
+    """ForceStressOutput (grad_output.py:162-268): stress/virial from the per-edge gradients == the oracle's
+    displacement-trick autograd; plus a finite-difference check of dE/d(strain) in float64."""
+    model, sysd = _build("water_l2_f32", dtype, n_side=5, seed=5)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    dev = D.to_device(sysd, "cuda")
+    out = model(dev, compute_stress=True)
+    e_ref, f_ref, s_ref, v_ref = omodel.energy_forces_stress(model.state_dict(), model.config, sysd, dtype)
+    assert out["stress"].shape == (1, 3, 3) and out["virial"].shape == (1, 3, 3)
+    sscale = float(s_ref.abs().max())
+    assert float((out["stress"].cpu() - s_ref).abs().max()) <= tol * sscale, float((out["stress"].cpu() - s_ref).abs().max()) / sscale
+    assert float((out["virial"].cpu() - v_ref).abs().max()) <= tol * float(v_ref.abs().max())
+    assert float((out["forces"].cpu() - f_ref).abs().max()) <= tol * float(f_ref.abs().max())
+    if dtype == torch.float64:
+        eps = 1e-5
+        vol = float(torch.linalg.det(sysd["cell"]).abs())
+        for (a, b) in [(0, 0), (0, 1), (2, 1)]:
+            es = []
+            for sgn in (+1, -1):
+                strain = torch.zeros(3, 3, dtype=torch.float64)
+                strain[a, b] += sgn * eps / 2
+                strain[b, a] += sgn * eps / 2
+                d2 = dict(dev)
+                d2["pos"] = dev["pos"] @ (torch.eye(3, dtype=torch.float64) + strain).cuda()
+                d2["cell"] = dev["cell"] @ (torch.eye(3, dtype=torch.float64) + strain).cuda()
+                es.append(float(model(d2, compute_forces=False)["total_energy"]))
+            fd = (es[0] - es[1]) / (2 * eps) / vol  # dE/d(eps_ab) symmetrised
+            got = float(out["stress"][0, a, b])
+            assert abs(fd - got) <= 1e-6 * max(abs(fd), float(out["stress"].abs().max())), (a, b, fd, got)
+
+
+def test_edge_force_branch_matches_oracle():
+    """ML-IAP branch (grad_output.py:270-296): edge_vectors in -> edge_forces = dE/d(edge_vectors) out."""
+    model, sysd = _build("water_l2_f32", torch.float32, n_side=5, seed=6)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    vec = omodel.edge_vectors(sysd["pos"], sysd["edge_index"], sysd["cell"], sysd["edge_cell_shift"])
+    d = {k: v for k, v in sysd.items() if k not in ("cell", "edge_cell_shift")}
+    d["edge_vectors"] = vec
+    out = model(D.to_device(d, "cuda"))
+    e_ref, g_ref = omodel.edge_forces(model.state_dict(), model.config, d, torch.float32)
+    assert out["edge_forces"].shape == vec.shape and "forces" not in out
+    assert float((out["edge_forces"].cpu() - g_ref).abs().max()) <= 1e-5 * float(g_ref.abs().max())
+    # same energy as the position-based evaluation of the same frame
+    e_pos = model(D.to_device(sysd, "cuda"), compute_forces=False)["total_energy"]
+    assert abs(float(out["total_energy"]) - float(e_pos)) <= 1e-6 * float(out["atomic_energy"].abs().sum())
+    assert abs(float(out["total_energy"]) - float(e_ref)) <= 1e-5 * float(out["atomic_energy"].abs().sum())

@@ -35,12 +35,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, sysd, ret):
+def _worker(rank, world, port, sysd, ret, grid=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        owner = P.slab_owner(sysd["pos"], world)
+        owner = P.slab_owner(sysd["pos"], world) if grid is None else P.brick_owner(sysd["pos"], grid)
         plan = P.make_plans(sysd["edge_index"], owner, world)[rank]
         local = P.shard_data(sysd, plan)
         halo = P.HaloExchange(plan, "cpu")
@@ -54,6 +54,10 @@ def _worker(rank, world, port, sysd, ret):
         f = torch.zeros(plan.num_global, 3, dtype=torch.float64)
         f.index_add_(0, plan.local_ids, -g)
         dist.all_reduce(f)
+        # owner reduction (what the product uses at scale): ghost gradients travel back to their owners
+        f_own = -P.owner_reduce(g, plan, halo)
+        assert f_own.shape == (plan.n_own, 3)
+        torch.testing.assert_close(f_own, f[plan.owned], atol=1e-12, rtol=1e-10)
         if rank == 0:
             ret["e"], ret["f"] = e, f
             ret["ghost_frac"] = plan.n_ghost / max(plan.n_own, 1)
@@ -62,8 +66,8 @@ def _worker(rank, world, port, sysd, ret):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_toy_model_matches_single_process(world):
+@pytest.mark.parametrize("world,grid", [(2, None), (3, None), (4, (2, 2, 1))])
+def test_sharded_toy_model_matches_single_process(world, grid):
     sysd = D.make_system("water", 6, r_max=5.0, seed=4)
     sysd.pop("_meta")
     # single process reference (world 1: halo is the identity)
@@ -75,7 +79,7 @@ def test_sharded_toy_model_matches_single_process(world):
     (g_ref,) = torch.autograd.grad(e_ref, pos)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), sysd, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), sysd, ret, grid), nprocs=world, join=True)
     assert abs(float(ret["e"]) - float(e_ref)) < 1e-10 * max(1.0, abs(float(e_ref)))
     torch.testing.assert_close(ret["f"], -g_ref.detach(), atol=1e-11, rtol=1e-9)
     assert ret["ghost_frac"] > 0
@@ -97,3 +101,17 @@ def test_plans_are_consistent():
         # edges are the global edges with owned destination, re-indexed
         ge = sysd["edge_index"][:, p.edge_ids]
         assert torch.equal(p.local_ids[p.edge_index[0]], ge[0]) and torch.equal(p.local_ids[p.edge_index[1]], ge[1])
+
+
+def test_brick_decomposition():
+    sysd = D.make_system("li3po4", 8, r_max=5.0, seed=1)
+    pos = sysd["pos"]
+    assert torch.equal(P.brick_owner(pos, (4, 1, 1)), P.slab_owner(pos, 4))
+    owner = P.brick_owner(pos, (2, 2, 2))
+    assert torch.bincount(owner, minlength=8).tolist() == [64] * 8
+    plans = P.make_plans(sysd["edge_index"], owner, 8)
+    assert sum(p.n_own for p in plans) == pos.shape[0]
+    # elongated boxes are cut into slabs, cubic boxes into bricks (fewest ghosts for a 5 A halo)
+    assert P.brick_grid(8, [374.0, 46.8, 46.8]) == (8, 1, 1)
+    g = P.brick_grid(8, [93.6, 93.6, 93.6])
+    assert g[0] * g[1] * g[2] == 8 and max(g) < 8

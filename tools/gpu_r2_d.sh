@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_tp_fused_gpu.py -x -q > gpurun_out/r2d_fused_tests.txt 2>&1; echo "rc=$?" >> gpurun_out/r2d_fused_tests.txt
+tail -6 gpurun_out/r2d_fused_tests.txt
+timeout 600 python tools/bench_fused.py --prof > gpurun_out/r2d_bench_fused.jsonl 2> gpurun_out/r2d_bench_fused.err; echo "rc=$?" >> gpurun_out/r2d_bench_fused.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2d_bench_fused.jsonl'):
+    d=json.loads(l); p=d.pop('prof_first_cta_of_slice',None); c=d.pop('cta_total_Mcycles',None)
+    print(d)
+    if p:
+        for r in p: print('   ', r)
+    if c: print('    cta Mcycles min/max', min(c), max(c))
+PY
+tail -3 gpurun_out/r2d_bench_fused.err
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2d_tests.txt 2>&1; echo "rc=$?" >> gpurun_out/r2d_tests.txt
+tail -6 gpurun_out/r2d_tests.txt
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2d_bench.json 2> gpurun_out/r2d_bench.err
+cut -c1-300 gpurun_out/r2d_bench.json; tail -3 gpurun_out/r2d_bench.err
