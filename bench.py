@@ -105,18 +105,6 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the largest captured launch of ``kernel`` from the committed
-    ``ncu --set full`` summary (profiles/r01_ncu_full_summary.json, written from gpurun_out/final_*.raw.csv)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
-    try:
-        rows = json.load(open(p))[kernel]
-        r = max(rows, key=lambda x: x["ms"])
-        return int(round((r["dram_read_GB"] + r["dram_write_GB"]) * 1e9))
-    except Exception:
-        return None
-
-
 def tp_algorithmic_bytes(sig, N, E, elem=4, backward=False):
     """forward reads x, edge_attr, edge_weight, two int64 index arrays, writes out."""
     b = elem * (N * sig.d_in + E * sig.s_dim + E * sig.weight_numel + N * sig.d_out) + 16 * E
@@ -227,6 +215,160 @@ def cpu_baseline(workload):
     return {"value": n_atoms / dt, "unit": "atom-steps/s", "cores": cores, "kind": "port",
             "sample": (f"{n_atoms}-atom {WORKLOADS[workload][0]} box (same model, density, r_max), {reps} steps, "
                        f"E={sysd['edge_index'].shape[1]}, {cores} of {os.cpu_count()} host threads (fastest of a short sweep)")}
+
+
+def ncu_summary(kernel, field):
+    """A per-launch metric of ``kernel`` from the committed ``ncu --set full`` summaries of this round
+    (profiles/r02_ncu_full_summary.json; falls back to round 1's), or None."""
+    for name in ("r02_ncu_full_summary.json", "r01_ncu_full_summary.json"):
+        try:
+            rows = json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]
+            r = max(rows, key=lambda x: x["ms"])
+            if field == "traffic":
+                return int(round((r["dram_read_GB"] + r["dram_write_GB"]) * 1e9))
+            return r.get(field)
+        except Exception:
+            continue
+    return None
+
+
+def _time_cuda(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def kernel_rooflines(model, resident, n_atoms, n_edges, reps, ms_step, dev):
+    """Isolated timing of the hot kernels of every interaction layer with the step's shapes.
+
+    Algorithmic bytes (SURVEY.md section 8d / DESIGN.md section 4): TP forward  4 (N D_in + E S + E W + N D_mid) + 16 E,
+    TP backward 4 (N D_mid + 2 N D_in + 2 E S + 2 E W) + 16 E, radial GEMM 4 E (K + W) + 4 K W; the fused forward
+    kernel reads 4 (N D_in + E S + E K) + 16 E + weights and writes 4 N D_mid (+ 4 E W when the weights are kept for
+    the backward).  Tensor work of the 3xTF32 GEMMs: 3 x 2 E K W flop."""
+    from nequip_b200 import ops
+    from nequip_b200.nn import dense
+    from nequip_b200.nn.model import ScalarLinearLayer
+
+    peak_hbm, peak_src = load_peaks()
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        tf32_peak = float(pk["bf16_tflops_sustained"]) / 2.0  # no TF32 measurement exists: half the measured bf16 rate
+        tf32_src = "estimated: measured sustained bf16 cuBLAS rate / 2"
+    except Exception:
+        tf32_peak, tf32_src = 1590.0 / 2.0, "estimated: fallback bf16 rate / 2"
+    N, E = n_atoms, n_edges
+    ei = resident["edge_index"]
+    csr = ops.build_csr(ei[0].contiguous(), N)
+    src = ei[1].contiguous()
+    g = torch.Generator(device=dev).manual_seed(0)
+    classes = {}
+
+    def add(cls, entry):
+        c = classes.setdefault(cls, {"ms_per_step": 0.0, "launches_per_step": 0, "largest": None})
+        c["ms_per_step"] += entry["ms_per_launch"]
+        c["launches_per_step"] += 1
+        if c["largest"] is None or entry["ms_per_launch"] > c["largest"]["ms_per_launch"]:
+            c["largest"] = entry
+
+    def hbm_entry(kernel, ms, alg, layer, extra=None):
+        ach = alg / (ms * 1e-3) / 1e9
+        d = {"kernel": kernel, "layer": layer, "bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
+             "frac": ach / peak_hbm, "alg_bytes_per_launch": alg, "ms_per_launch": ms}
+        if extra:
+            d.update(extra)
+        return d
+
+    with torch.no_grad():
+        for li, layer in enumerate(model.layers):
+            conv = layer.conv
+            plan = conv.tp_scatter._plan
+            sig = plan.sig
+            W, K = sig.weight_numel, 128
+            lins = [m for m in conv.edge_mlp.mlp if isinstance(m, ScalarLinearLayer)]
+            if len(lins) != 2 or not dense.RadialMLPGemm.supported(lins[0], lins[1], torch.float32):
+                continue
+            K = lins[1].weight.shape[0]
+            x = torch.randn(N, sig.d_in, device=dev, generator=g)
+            y = torch.randn(E, sig.s_dim, device=dev, generator=g)
+            emb = torch.rand(E, lins[0].weight.shape[0], device=dev, generator=g)
+            go = torch.randn(N, sig.d_out, device=dev, generator=g)
+            mlp = dense.RadialMLPGemm(lins[0], lins[1], dev)
+            h = torch.nn.functional.silu(emb @ mlp.w1s)
+            w = torch.empty(E, W, device=dev)
+            gh = torch.empty(E, K, device=dev)
+            flops3 = 3 * 2.0 * E * K * W
+            tc = conv._tc_cache[1] if conv._tc_cache else None
+            fused = tc["fused"] if (tc and conv.use_fused_radial_tp) else None
+            if fused is not None:
+                ms = _time_cuda(lambda: ops.tp_fused_fwd(fused.fw, x, y, h, src, csr, want_w=True), reps)
+                alg = 4 * (N * sig.d_in + E * sig.s_dim + E * K + N * sig.d_out + E * W) + 16 * E + 8 * K * W
+                tfl = flops3 / (ms * 1e-3) / 1e12
+                add("tp_fused_fwd_kernel", hbm_entry("tp_fused_fwd_kernel (radial GEMM + TP + scatter, tcgen05 + FFMA2)", ms, alg, li, {
+                    "tensor": {"achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s (3xTF32 issue)", "frac": tfl / tf32_peak,
+                               "peak_source": tf32_src}}))
+            else:
+                ms = _time_cuda(lambda: mlp.fwd.run(h, w, E), reps)
+                alg = 4 * E * (K + W) + 8 * K * W
+                tfl = flops3 / (ms * 1e-3) / 1e12
+                add("k_gemm3x", hbm_entry("k_gemm3x (radial MLP last layer forward, tcgen05 3xTF32)", ms, alg, li, {
+                    "tensor": {"achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s (3xTF32 issue)", "frac": tfl / tf32_peak,
+                               "peak_source": tf32_src,
+                               "pipe_tensor_cycles_active_pct": ncu_summary("k_gemm3x", "pipe_tensor_pct")}}))
+                ms = _time_cuda(lambda: ops.tp_scatter(plan, x, y, w, ei[0], src, csr=csr), reps)
+                name = "tp_fwd2_kernel" if TPGen(sig, plan.opts).ring_fwd() else "tp_fwd_kernel<float>"
+                add(name, hbm_entry(name + " (fused TP + scatter forward)", ms, tp_algorithmic_bytes(sig, N, E), li))
+            # backward: TP + scatter, then the radial GEMM for grad_h
+            ms = _time_cuda(lambda: ops.tp_scatter_bwd_raw(plan, x, y, w, src, csr, go, need_x=(li != 0)), reps)
+            name = "tp_bwd2_kernel" if TPGen(sig, plan.opts).ring_bwd() else "tp_bwd_kernel<float>"
+            add(name, hbm_entry(name + " (fused TP + scatter backward; incl. the zero fills of grad_x / grad_Y)", ms,
+                                tp_algorithmic_bytes(sig, N, E, backward=True), li,
+                                {"fma": {"note": "FP32-FMA bound for l_max >= 2 layers", "mults_per_edge_channel_fwd": sig.fma_count()}}))
+            ms = _time_cuda(lambda: mlp.bwd.run(w, gh, E), reps)
+            alg = 4 * E * (K + W) + 8 * K * W
+            tfl = flops3 / (ms * 1e-3) / 1e12
+            add("k_gemm3x", hbm_entry("k_gemm3x (radial MLP last layer backward, K = W)", ms, alg, li, {
+                "tensor": {"achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s (3xTF32 issue)", "frac": tfl / tf32_peak,
+                           "peak_source": tf32_src,
+                           "pipe_tensor_cycles_active_pct": ncu_summary("k_gemm3x", "pipe_tensor_pct")}}))
+            del x, y, emb, go, h, w, gh
+    for k, c in classes.items():
+        c["share_of_step"] = c["ms_per_step"] / ms_step
+    top_name = max(classes, key=lambda k: classes[k]["ms_per_step"])
+    top = dict(classes[top_name]["largest"])
+    top["traffic"] = ncu_summary(top_name.split("<")[0], "traffic")
+    top["peak_source"] = peak_src
+    top["share_of_step"] = classes[top_name]["share_of_step"]
+    top["selection"] = ("kernel class with the largest summed isolated time over the layers of one step; numbers are for "
+                        "its largest launch")
+    top["inputs"] = "per-edge operands of the step's size (>> 126 MB L2)"
+    top["by_kernel"] = {k: {"ms_per_step_isolated": c["ms_per_step"], "share_of_step": c["share_of_step"],
+                            "launches_per_step": c["launches_per_step"],
+                            "traffic": ncu_summary(k.split("<")[0], "traffic"), **c["largest"]}
+                        for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+    return top
+
+
+class TPGen:
+    """Which forward / backward kernel variant the generator picked for a signature."""
+
+    def __init__(self, sig, opts):
+        from nequip_b200.codegen import TPGenerator
+
+        self.g = TPGenerator(sig, opts)
+        self.g.source()
+
+    def ring_fwd(self):
+        return bool(self.g.use_ring)
+
+    def ring_bwd(self):
+        return bool(self.g.use_ring_bwd)
 
 
 def main():
@@ -416,60 +558,12 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     d2h = f_host.numel() * 8 + 8
 
-    # ---- roofline of the dominant kernel: fused TP+scatter forward of the largest layer, alone
+    # ---- rooflines, measured live: every hot kernel class of every layer is timed ALONE (CUDA events on the
+    # launching stream, inputs of the step's shapes, > L2); the class with the largest share of the step is the
+    # headline `roofline`, the others are listed under `roofline.by_kernel`
     roof = None
     if rank == 0:
-        peak, peak_src = load_peaks()
-        layer = max(model.layers, key=lambda l: l.conv.tp_scatter.weight_numel)
-        tps = layer.conv.tp_scatter
-        sig = tps._plan.sig
-        g = torch.Generator(device=dev).manual_seed(0)
-        x = torch.randn(n_atoms, sig.d_in, device=dev, generator=g)
-        y = torch.randn(n_edges, sig.s_dim, device=dev, generator=g)
-        w = torch.randn(n_edges, sig.weight_numel, device=dev, generator=g)
-        ei = resident["edge_index"]
-        csr = ops.build_csr(ei[0].contiguous(), n_atoms)
-        src = ei[1].contiguous()
-        with torch.no_grad():
-            for _ in range(3):
-                ops.tp_scatter(tps._plan, x, y, w, ei[0], src, csr=csr)
-            torch.cuda.synchronize()
-            reps = max(5, args.steps)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                ops.tp_scatter(tps._plan, x, y, w, ei[0], src, csr=csr)
-            e1.record()
-            torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
-        alg = tp_algorithmic_bytes(sig, n_atoms, n_edges)
-        ach = alg / (k_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ncu_traffic("tp_fwd2_kernel"),  # dram read+write bytes per launch (ncu --set full), or None
-                "kernel": "tp_fwd_kernel<float> (fused TP+scatter forward)", "layer_signature_W": sig.weight_numel,
-                "alg_bytes_per_launch": alg, "ms_per_launch": k_ms, "peak_source": peak_src,
-                "inputs": "w stream %.2f GB >> 126 MB L2" % (n_edges * sig.weight_numel * 4 / 1e9)}
-        # backward kernel too (reported, not the headline roofline)
-        xg = x.clone().requires_grad_(True)
-        yg = y.clone().requires_grad_(True)
-        wg = w.clone().requires_grad_(True)
-        out = ops.tp_scatter(tps._plan, xg, yg, wg, ei[0], src, csr=csr)
-        go = torch.randn_like(out)
-        for _ in range(2):
-            torch.autograd.grad(out, [xg, yg, wg], go, retain_graph=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            torch.autograd.grad(out, [xg, yg, wg], go, retain_graph=True)
-        e1.record()
-        torch.cuda.synchronize()
-        b_ms = e0.elapsed_time(e1) / reps
-        algb = tp_algorithmic_bytes(sig, n_atoms, n_edges, backward=True)
-        roof["backward"] = {"ms_per_launch": b_ms, "alg_bytes_per_launch": algb,
-                            "achieved": algb / (b_ms * 1e-3) / 1e9, "frac": algb / (b_ms * 1e-3) / 1e9 / peak,
-                            "traffic": ncu_traffic("tp_bwd2_kernel"), "note": "includes torch.zeros_like for grad_x/grad_y"}
-        del x, y, w, xg, yg, wg, out, go
-
+        roof = kernel_rooflines(model, resident, n_atoms, n_edges, max(5, args.steps), ms_res, dev)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
         cpu = cpu_baseline(args.workload)

@@ -94,7 +94,18 @@ int nqb_tp_scatter_fwd(const nqb_plan* plan, int dtype, const void* x, const voi
 int nqb_tp_scatter_bwd(const nqb_plan* plan, int dtype, const void* x, const void* y, const void* w,
                        const int64_t* row_ptr, const int64_t* perm, const int64_t* src,
                        const void* grad_out, int64_t N, int64_t E, void* grad_x, void* grad_y,
-                       void* grad_w, nqb_stream_t st);
+                       void* grad_w, int deterministic,
+                       nqb_stream_t st);
+/* deterministic != 0 (bitwise-repeatable backward; the default accumulates grad_x / grad_Y with red.global.add in
+ * whatever order the edges retire, as the reference's OpenEquivariance back-end does, nequip/nn/_tp_scatter_oeq.py:46):
+ *   grad_x is then an [E, D_in] buffer -- every edge stores its contribution to its SOURCE atom in its own row -- to be
+ *   reduced over the source-sorted edges with nqb_segment_sum (perm = stable argsort of edge_src, the
+ *   edge_transpose_perm of nequip/data/transforms/neighborlist.py:150-155; seg_ptr = CSR over the sorted sources);
+ *   grad_y is [nqb_tp_scatter_gy_slices(plan, dtype), E, S], zero-initialised by the caller: each writer owns a slice,
+ *   the caller sums the slices in index order. */
+int nqb_tp_scatter_gy_slices(const nqb_plan* plan, int dtype);
+int nqb_segment_sum(int dtype, const void* rows /* [R, D] */, int D, const int64_t* perm, const int64_t* seg_ptr /* [N+1] */,
+                    int64_t N, void* out /* [N, D] */, nqb_stream_t st);
 
 /* Fused "last radial-MLP layer -> tensor product -> scatter" forward:
  *   out[n] = sum_{e: dst[e] = n} TP_uvu(x[src[e]], y[e], w[e]),   w[e] = h[e, :K] @ (W2 * alpha2)

@@ -42,7 +42,9 @@ SIGNATURES = {
     "nqb_csr_from_sorted": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "nqb_tp_scatter_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "nqb_tp_scatter_bwd": (
-        _i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+        _i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "nqb_tp_scatter_gy_slices": (_i32, [_vp, _i32]),
+    "nqb_segment_sum": (_i32, [_i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     "nqb_tp_fused_slices": (_i32, [_vp]),
     "nqb_tp_fused_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
     "nqb_nl_bin": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),

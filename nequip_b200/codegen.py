@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 16
+CODEGEN_VERSION = 18
 
 
 # ---------------------------------------------------------------------------
@@ -590,7 +590,7 @@ class TPGenerator:
             "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
             "const int64_t* __restrict__ perm, const int64_t* __restrict__ src, const T* __restrict__ gout, "
             "int64_t n, int64_t beg, int64_t end, int ch0, int sub, int cl, "
-            "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw)"
+            "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw, bool det)"
         )
         em("typedef typename VT<T>::V V; constexpr int EPW = VT<T>::EPW; constexpr int LPE = VT<T>::LPE;")
         self._emit_bwd_prologue(em, paths)
@@ -691,25 +691,33 @@ class TPGenerator:
                     al = "true" if (sig.weight_numel % 2 == 0 and p.woff % 2 == 0) else "false"
                     em(f"if (valid) vstorew<{p.mul}, {al}>(gw + e * {sig.weight_numel} + {p.woff} + ch0, r{p.idx}, ch0);")
             em.end()
-        # grad_x: atomics into the source row
+        # grad_x: atomics into the source row -- or, in deterministic mode, plain stores into the EDGE's own row of a
+        # [E, D_in] buffer that nqb_segment_sum reduces over the (source-sorted) edges in a fixed order
         em.block("if (WANT_GX && valid)")
+        em("const int64_t gxr = det ? e : sn;")
         for i1 in sorted({p.i1 for p in paths}):
             mul, ir = sig.irreps_in1[i1]
             n1 = ir.dim
             xoff = sig.irreps_in1.offsets()[i1]
             if self.opts.layout == "ir_mul":
                 al = "true" if (self.opts.red_v2 and sig.d_in % 2 == 0 and xoff % 2 == 0 and mul % 2 == 0) else "false"
-                em(f"T* gxp{i1} = gx + sn * {sig.d_in} + {xoff} + ch0;")
+                em(f"T* gxp{i1} = gx + gxr * {sig.d_in} + {xoff} + ch0;")
                 for i in range(n1):
-                    em(f"vatomicc<{mul}, {al}>(gxp{i1} + {i * mul}, d{i1}_{i}, ch0);")
+                    em(f"if (det) vstorew<{mul}, {al}>(gxp{i1} + {i * mul}, d{i1}_{i}, ch0); else vatomicc<{mul}, {al}>(gxp{i1} + {i * mul}, d{i1}_{i}, ch0);")
                 continue
-            em(f"T* gxp{i1} = gx + sn * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
+            em(f"T* gxp{i1} = gx + gxr * {sig.d_in} + {xoff} + (int64_t)ch0 * {n1};")
+            em.block("if (det)")
+            for i in range(n1):
+                em(f"vstore<{n1}, {mul}>(gxp{i1} + {i}, d{i1}_{i}, ch0);")
+            em.end()
+            em.block("else")
             if self.opts.red_v2 and sig.d_in % 2 == 0 and xoff % 2 == 0:
                 args = ", ".join(f"d{i1}_{i}" for i in range(n1))
                 em(f"vatomic_row<{n1}, {mul}>(gxp{i1}, ch0, {args});")
             else:
                 for i in range(n1):
                     em(f"vatomic<{n1}, {mul}>(gxp{i1} + {i}, d{i1}_{i}, ch0);")
+            em.end()
         em.end()
         # grad_Y: halving reduce-scatter over the lanes that share this edge, then one atomic per component
         y0, y1 = yused[0], yused[-1] + 1
@@ -734,7 +742,7 @@ class TPGenerator:
             "const int64_t* __restrict__ perm, const int64_t* __restrict__ src, const float* __restrict__ gout, "
             "int64_t n, int64_t beg, int64_t end, int ch0, int sub, int cl, int warp, int lane, "
             "float* ring, uint64_t* full, uint64_t* empty, int64_t* eids, int64_t* srcs, "
-            "float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gw)"
+            "float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gw, bool det)"
         )
         em("typedef float T; typedef VT<float>::V V; constexpr int EPW = VT<float>::EPW; constexpr int LPE = VT<float>::LPE;")
         self._emit_bwd_prologue(em, paths)
@@ -1092,7 +1100,7 @@ class TPGenerator:
             "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
             "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
             "const int64_t* __restrict__ src, const T* __restrict__ gout, int64_t N, "
-            "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw)"
+            "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw, int det, int64_t gy_slice)"
         )
         em("constexpr int CB = VT<T>::CB, LPE = VT<T>::LPE, CPT = VT<T>::CPT;")
         em("const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
@@ -1106,7 +1114,7 @@ class TPGenerator:
         for gid in range(len(self.bwd_groups)):
             em(
                 f"case {gid}: bwd_g{gid}<T, WANT_GX>(x, y, w, perm, src, gout, n, beg, end, ch0, sub, cl, "
-                "gx, gy, gw); break;"
+                "gx, gy + (int64_t)blockIdx.y * gy_slice, gw, det != 0); break;"
             )
         em("default: break;")
         em.end()
@@ -1118,7 +1126,7 @@ class TPGenerator:
                 "const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w, "
                 "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
                 "const int64_t* __restrict__ src, const float* __restrict__ gout, int64_t N, "
-                "float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gw)"
+                "float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gw, int det, int64_t gy_slice)"
             )
             em("extern __shared__ __align__(16) uint8_t b2_smem[];")
             em("constexpr int LPE = VT<float>::LPE, CPT = VT<float>::CPT, EPW = VT<float>::EPW;")
@@ -1142,7 +1150,7 @@ class TPGenerator:
             em.block("switch (warp)")
             for gid in range(len(self.bwd_groups)):
                 em(f"case {gid}: bwd2_g{gid}<WANT_GX>(x, y, w, perm, src, gout, n, beg, end, ch0, sub, cl, warp, lane, "
-                   "ring, full, empty, eids, srcs, gx, gy, gw); break;")
+                   "ring, full, empty, eids, srcs, gx, gy + (int64_t)(warp * gridDim.y + blockIdx.y) * gy_slice, gw, det != 0); break;")
             em("default: break;")
             em.end()
             em.end()
@@ -1190,10 +1198,10 @@ class TPGenerator:
         em.block(
             'extern "C" int nqb_spec_bwd(int dtype, const void* x, const void* y, const void* w, '
             "const int64_t* row_ptr, const int64_t* perm, const int64_t* src, const void* gout, "
-            "int64_t N, int64_t E, void* gx, void* gy, void* gw, cudaStream_t st)"
+            "int64_t N, int64_t E, void* gx, void* gy, void* gw, int det, cudaStream_t st)"
         )
-        em("(void)E;")
         em("if (N <= 0) return 0;")
+        em(f"const int64_t gy_slice = det ? E * {sig.s_dim} : 0;  // deterministic: one grad_Y slice per (path group, channel block)")
         em("dim3 block(32 * NWARP);")
         if self.use_ring_bwd:
             lpe_f2, epw_f2, cb_f2 = self.geometry(2)
@@ -1210,7 +1218,7 @@ class TPGenerator:
             em.end()
             em("dim3 grid2((unsigned)N, VT<float>::CB), block2(32 * NGB);")
             a2 = ("(const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, (const float*)gout, N, "
-                  "(float*)gx, (float*)gy, (float*)gw")
+                  "(float*)gx, (float*)gy, (float*)gw, det, gy_slice")
             em(f"if (gx) tp_bwd2_kernel<true><<<grid2, block2, B2_SMEM, st>>>({a2});")
             em(f"else tp_bwd2_kernel<false><<<grid2, block2, B2_SMEM, st>>>({a2});")
             em("return (int)cudaGetLastError();")
@@ -1220,12 +1228,18 @@ class TPGenerator:
             em(f"dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGB * VT<{name}>::CB);")
             args = (
                 f"(const {name}*)x, (const {name}*)y, (const {name}*)w, row_ptr, perm, src, "
-                f"(const {name}*)gout, N, ({name}*)gx, ({name}*)gy, ({name}*)gw"
+                f"(const {name}*)gout, N, ({name}*)gx, ({name}*)gy, ({name}*)gw, det, gy_slice"
             )
             em(f"if (gx) tp_bwd_kernel<{name}, true><<<grid, block, 0, st>>>({args});")
             em(f"else tp_bwd_kernel<{name}, false><<<grid, block, 0, st>>>({args});")
             em.end()
         em("return (int)cudaGetLastError();")
+        em.end()
+        # deterministic mode: number of grad_Y slices (one per (path group, channel block) writer)
+        em.block('extern "C" int nqb_spec_gy_slices(int dtype)')
+        if self.use_ring_bwd:
+            em("if (dtype == 0) return NGB * VT<float>::CB;")
+        em("return dtype == 0 ? NGB * VT<float>::CB : NGB * VT<double>::CB;")
         em.end()
         # fused radial-MLP last layer + TP + scatter forward; -1 = not built for this signature
         em.block('extern "C" int nqb_spec_fused_info(int* nslice, int* nxs, int* xrow)')

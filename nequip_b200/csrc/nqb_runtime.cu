@@ -65,8 +65,9 @@ typedef int (*spec_version_fn)();
 typedef int (*spec_dims_fn)(int*, int*, int*, int*);
 typedef int (*spec_fwd_fn)(int, const void*, const void*, const void*, const int64_t*, const int64_t*,
                            const int64_t*, int64_t, int64_t, void*, cudaStream_t);
+typedef int (*spec_gy_slices_fn)(int);
 typedef int (*spec_bwd_fn)(int, const void*, const void*, const void*, const int64_t*, const int64_t*,
-                           const int64_t*, const void*, int64_t, int64_t, void*, void*, void*, cudaStream_t);
+                           const int64_t*, const void*, int64_t, int64_t, void*, void*, void*, int, cudaStream_t);
 
 typedef int (*spec_fused_info_fn)(int*, int*, int*);
 typedef int (*spec_fused_fwd_fn)(const float*, const float*, const float*, int64_t, int, const float*, const int64_t*,
@@ -77,6 +78,7 @@ struct nqb_plan {
   void* lib;
   spec_fwd_fn fwd;
   spec_bwd_fn bwd;
+  spec_gy_slices_fn gy_slices = nullptr;
   spec_fused_fwd_fn fused_fwd = nullptr;  // null: the signature has no fused radial-MLP + TP kernel
   int fused_nslice = 0;
   int d_in, s_dim, w_numel, d_out;
@@ -140,6 +142,7 @@ extern "C" int nqb_plan_create(const nqb_irrep* in1, int n_in1, const nqb_irrep*
   p->fwd = ffwd;
   p->bwd = fbwd;
   fdims(&p->d_in, &p->s_dim, &p->w_numel, &p->d_out);
+  p->gy_slices = (spec_gy_slices_fn)dlsym(lib, "nqb_spec_gy_slices");
   spec_fused_info_fn finfo = (spec_fused_info_fn)dlsym(lib, "nqb_spec_fused_info");
   spec_fused_fwd_fn ffused = (spec_fused_fwd_fn)dlsym(lib, "nqb_spec_fused_fwd");
   int nxs = 0, xrow = 0;
@@ -192,16 +195,52 @@ extern "C" int nqb_tp_scatter_fwd(const nqb_plan* plan, int dtype, const void* x
 extern "C" int nqb_tp_scatter_bwd(const nqb_plan* plan, int dtype, const void* x, const void* y, const void* w,
                                   const int64_t* row_ptr, const int64_t* perm, const int64_t* src,
                                   const void* grad_out, int64_t N, int64_t E, void* grad_x, void* grad_y,
-                                  void* grad_w, nqb_stream_t st) {
+                                  void* grad_w, int deterministic, nqb_stream_t st) {
   if (!plan) return fail("nqb_tp_scatter_bwd: null plan");
   if (dtype != NQB_F32 && dtype != NQB_F64) return fail("nqb_tp_scatter_bwd: bad dtype %d", dtype);
   if (N < 0 || E < 0) return fail("nqb_tp_scatter_bwd: negative size");
   if (N == 0 || E == 0) return 0;
   if (!row_ptr || !x || !y || !w || !src || !grad_out || !grad_y || !grad_w)
     return fail("nqb_tp_scatter_bwd: null pointer argument");
-  int rc = plan->bwd(dtype, x, y, w, row_ptr, perm, src, grad_out, N, E, grad_x, grad_y, grad_w, (cudaStream_t)st);
+  if (deterministic && !plan->gy_slices) return fail("nqb_tp_scatter_bwd: kernel library has no deterministic mode");
+  int rc = plan->bwd(dtype, x, y, w, row_ptr, perm, src, grad_out, N, E, grad_x, grad_y, grad_w, deterministic ? 1 : 0,
+                     (cudaStream_t)st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (rc) return cuda_fail((cudaError_t)rc, "nqb_tp_scatter_bwd launch");
+  return 0;
+}
+
+extern "C" int nqb_tp_scatter_gy_slices(const nqb_plan* plan, int dtype) {
+  if (!plan || !plan->gy_slices) return 0;
+  return plan->gy_slices(dtype);
+}
+
+// out[n, :] = sum over the rows perm[q], q in [seg_ptr[n], seg_ptr[n+1]), of rows[., :]   (fixed order: deterministic)
+template <typename T>
+__global__ void k_segment_sum(const T* __restrict__ rows, int D, const int64_t* __restrict__ perm,
+                              const int64_t* __restrict__ seg_ptr, int64_t N, T* __restrict__ out) {
+  const int64_t n = blockIdx.x;
+  if (n >= N) return;
+  const int64_t beg = seg_ptr[n], end = seg_ptr[n + 1];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    T acc = (T)0;
+    for (int64_t q = beg; q < end; ++q) acc += rows[perm[q] * (int64_t)D + c];
+    out[n * (int64_t)D + c] = acc;
+  }
+}
+
+extern "C" int nqb_segment_sum(int dtype, const void* rows, int D, const int64_t* perm, const int64_t* seg_ptr, int64_t N,
+                               void* out, nqb_stream_t st) {
+  if (dtype != NQB_F32 && dtype != NQB_F64) return fail("nqb_segment_sum: bad dtype %d", dtype);
+  if (N < 0 || D <= 0) return fail("nqb_segment_sum: bad size");
+  if (N == 0) return 0;
+  if (!rows || !perm || !seg_ptr || !out) return fail("nqb_segment_sum: null pointer");
+  const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
+  if (dtype == NQB_F32)
+    k_segment_sum<float><<<(unsigned)N, threads, 0, (cudaStream_t)st>>>((const float*)rows, D, perm, seg_ptr, N, (float*)out);
+  else
+    k_segment_sum<double><<<(unsigned)N, threads, 0, (cudaStream_t)st>>>((const double*)rows, D, perm, seg_ptr, N, (double*)out);
+  NQB_LAUNCH_CHECK("nqb_segment_sum");
   return 0;
 }
 

@@ -27,8 +27,10 @@
 //               end of a node set 1 hands its partial sums to set 0 through shared memory (fixed order: deterministic)
 //   warps 8-11  h producers: cp.async of the node's h rows (one tile ahead) + tf32 low part
 //   warp  12    MMA issue (one elected lane), TMEM allocation
-//   warp  13    x / Y stager: ONE cp.async.bulk per (edge, input chunk) -- an ir_mul chunk is contiguous -- with
-//               mbarrier complete_tx, and 4-byte cp.async for the Y pairs
+//   warps 13-15 x / Y stagers (stage xs belongs to stager xs % 3): 16-byte cp.async pieces of the gathered x rows
+//               (fixed lane -> piece map, source rows fetched one tile ahead) and 4-byte cp.async for the Y pairs.
+//               (One cp.async.bulk per (edge, chunk) was tried first: the bulk-copy unit retires only about one
+//               such request per 100-150 cycles per SM -- 9 k cycles per 55-edge tile, profiles/r02_fused_v2a.txt.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -165,6 +167,19 @@ __device__ __forceinline__ void ft_tmem_ld4x4(uint32_t t0, uint32_t t1, uint32_t
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 4 columns from each of two TMEM addresses, one wait
+__device__ __forceinline__ void ft_tmem_ld4x2(uint32_t t0, uint32_t t1, float* v) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%8];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [%9];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(t0), "r"(t1)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void ft_bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -196,56 +211,52 @@ __device__ __forceinline__ void ft_consumer(const FusedFwdArgs& a, FtSmem& S, co
       const uint32_t buf = it & 1;
       FTP_WAIT(0, mbar_wait(&S.acc_full[buf], (it >> 1) & 1))
       tc_fence_after();
+      // one 8-edge stage per iteration (rolled: the loop body must stay small -- with the stages unrolled the
+      // consumer, producer and stager code of one SM sub-partition exceeded its instruction cache and EVERY
+      // 128-byte line of instructions missed: 44 % of all stall samples were "no instruction",
+      // profiles/r02_ncu_fused_v2_stalls.txt)
 #pragma unroll 1
-      for (int c0 = 0; c0 < cnt; c0 += 16) {
-        // this set's weights of the two stages of the chunk: columns c0 + 4 set + {0..3} and c0 + 8 + 4 set + {0..3}
-        float w[8];
+      for (int e0 = 0; e0 < cnt; e0 += FT_SUB) {
+        // this set's weights of the stage: TMEM columns e0 + 4 set + {0..3} of the hi*hi and the cross-term accumulator
+        float w[4];
         {
-          float t[16];
-          const uint32_t b0 = tlane + 256 + buf * 128 + c0 + 4 * set;
-          FTP_WAIT(2, ft_tmem_ld4x4(b0, b0 + 64, b0 + 8, b0 + 8 + 64, t))
+          float t[8];
+          const uint32_t b0 = tlane + 256 + buf * 128 + e0 + 4 * set;
+          FTP_WAIT(2, ft_tmem_ld4x2(b0, b0 + 64, t))
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { w[j] = t[j] + t[4 + j]; w[4 + j] = t[8 + j] + t[12 + j]; }
+          for (int j = 0; j < 4; ++j) w[j] = t[j] + t[4 + j];
         }
-        if (c0 + 16 >= cnt) {  // every needed column of this buffer has been read
+        if (e0 + FT_SUB >= cnt) {  // every needed column of this buffer has been read
           tc_fence_before();
           mbar_arrive(&S.acc_empty[buf]);
         }
         if (P::ACTIVE && a.w_out != nullptr) {
-          float* wo = a.w_out + (t0 + c0 + 4 * set) * (int64_t)Spec::W + P::W_OFF + u;
+          float* wo = a.w_out + (t0 + e0 + 4 * set) * (int64_t)Spec::W + P::W_OFF + u;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int e = (j < 4) ? j : (j + 4);
-            if (c0 + 4 * set + e < cnt) wo[(int64_t)e * Spec::W] = w[j];
-          }
+          for (int j = 0; j < 4; ++j)
+            if (e0 + 4 * set + j < cnt) wo[(int64_t)j * Spec::W] = w[j];
         }
+        const uint32_t st = xs % NXS;
+        FTP_WAIT(1, mbar_wait(&S.x_full[st], (xs / NXS) & 1))
+        if (P::ACTIVE) {
+          // edges e0 + 4 set + {0,1} and {2,3}: no bounds tests -- an edge beyond the node has weight 0
+          const float* xb = xring + (size_t)st * STAGE_FLOATS + (4 * set) * XROW + P::XS_OFF + u;
+          const float2* yb = reinterpret_cast<const float2*>(xring + (size_t)st * STAGE_FLOATS + FT_SUB * XROW) +
+                             (2 * set) * SD + P::Y_OFF;
+          float2 xa[P::N1], ya[P::N2], xc[P::N1], yc[P::N2];
 #pragma unroll
-        for (int sb = 0; sb < 2; ++sb) {
-          const int e0 = c0 + sb * FT_SUB;
-          if (e0 < cnt) {
-            const uint32_t st = xs % NXS;
-            FTP_WAIT(1, mbar_wait(&S.x_full[st], (xs / NXS) & 1))
-            if (P::ACTIVE) {
-              // edges e0 + 4 set + {0,1} and {2,3}: no bounds tests -- an edge beyond the node has weight 0
-              const float* xb = xring + (size_t)st * STAGE_FLOATS + (4 * set) * XROW + P::XS_OFF + u;
-              const float2* yb = reinterpret_cast<const float2*>(xring + (size_t)st * STAGE_FLOATS + FT_SUB * XROW) +
-                                 (2 * set) * SD + P::Y_OFF;
-              float2 xa[P::N1], ya[P::N2], xc[P::N1], yc[P::N2];
-#pragma unroll
-              for (int i = 0; i < P::N1; ++i) {
-                xa[i] = make_float2(xb[i * P::MUL], xb[XROW + i * P::MUL]);
-                xc[i] = make_float2(xb[2 * XROW + i * P::MUL], xb[3 * XROW + i * P::MUL]);
-              }
-#pragma unroll
-              for (int j = 0; j < P::N2; ++j) { ya[j] = yb[j]; yc[j] = yb[SD + j]; }
-              P::fma(xa, ya, make_float2(w[sb * 4], w[sb * 4 + 1]), acc);
-              P::fma(xc, yc, make_float2(w[sb * 4 + 2], w[sb * 4 + 3]), acc);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.x_empty[st]);
-            ++xs;
+          for (int i = 0; i < P::N1; ++i) {
+            xa[i] = make_float2(xb[i * P::MUL], xb[XROW + i * P::MUL]);
+            xc[i] = make_float2(xb[2 * XROW + i * P::MUL], xb[3 * XROW + i * P::MUL]);
           }
+#pragma unroll
+          for (int j = 0; j < P::N2; ++j) { ya[j] = yb[j]; yc[j] = yb[SD + j]; }
+          P::fma(xa, ya, make_float2(w[0], w[1]), acc);
+          P::fma(xc, yc, make_float2(w[2], w[3]), acc);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.x_empty[st]);
+        ++xs;
       }
     }
     // node done: set 1 -> shared memory -> set 0 adds (always in this order) and writes the row
@@ -256,7 +267,7 @@ __device__ __forceinline__ void ft_consumer(const FusedFwdArgs& a, FtSmem& S, co
     ft_bar_consumers();
     if (P::ACTIVE && set == 0) {
 #pragma unroll
-      for (int k = 0; k < P::N3; ++k) acc[k].x = (acc[k].x + acc[k].y) + S.comb[slot][quad][k][lane];
+      for (int k = 0; k < P::N3; ++k) acc[k] = make_float2((acc[k].x + acc[k].y) + S.comb[slot][quad][k][lane], 0.f);
       FTP_WAIT(3, P::store(a.out + n * Spec::D_OUT, u, acc))
     }
 #pragma unroll
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
       mbar_init(&S.a_full[s], 128); mbar_init(&S.a_done[s], 1);
       mbar_init(&S.acc_full[s], 1); mbar_init(&S.acc_empty[s], 256);
     }
-    for (int s = 0; s < NXS; ++s) { mbar_init(&S.x_full[s], 33); mbar_init(&S.x_empty[s], 8); }
+    for (int s = 0; s < NXS; ++s) { mbar_init(&S.x_full[s], 32); mbar_init(&S.x_empty[s], 8); }
     mbar_init(&S.w_full, 128);
     fence_barrier_init();
     // which slice / node range
@@ -372,32 +383,41 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
     const int r8 = lane & 7, kq = lane >> 3;
     const int kgroups = ksteps * 2;  // 16-byte k-groups the MMAs read
     FTP_DECL
+    // thread -> rows rg * 8 + r8 (rg < nrg), k-groups kg = (pw + 4 j) * 4 + kq; all addresses by increments
+    const int kg0 = pw * 4 + kq, nkj = (kgroups - pw * 4 + 15) / 16;  // this warp's k-group blocks: kb = pw, pw + 4, ...
+    const int64_t rstep = 8 * a.ldh;
     auto issue_h = [&](uint32_t it, int64_t t0, int cnt) {
-      float* dst = S.hraw[it & 1];
+      float* dst0 = S.hraw[it & 1] + kg0 * 32 + r8 * 4;
+      const float* src0 = a.h + (t0 + r8) * a.ldh + kg0 * 4;
       const int nrg = ((cnt + 15) & ~15) / 8;  // 8-row groups the MMA reads (N rounded up to 16)
 #pragma unroll 1
-      for (int kb = pw; kb * 4 < kgroups; kb += 4) {
-        const int kg = kb * 4 + kq, k = kg * 4;
-#pragma unroll 2
+      for (int j = 0; j < nkj; ++j) {
+        float* dst = dst0 + j * (16 * 32);
+        const float* src = src0 + j * 64;
+#pragma unroll 1
         for (int rg = 0; rg < nrg; ++rg) {
-          const int m = rg * 8 + r8;
-          const bool in = m < cnt;
-          cp_async16(dst + rg * (FT_KMAX / 4 * 32) + kg * 32 + r8 * 4, a.h + (in ? (t0 + m) * a.ldh + k : 0), in ? 16u : 0u);
+          const bool in = rg * 8 + r8 < cnt;
+          cp_async16(dst, in ? src : a.h, in ? 16u : 0u);
+          dst += FT_KMAX / 4 * 32;
+          src += rstep;
         }
       }
     };
     auto lo_pass = [&](uint32_t it, int cnt) {
-      const float* raw = S.hraw[it & 1];
-      float* lo = S.hlo[it & 1];
+      const float* raw0 = S.hraw[it & 1] + kg0 * 32 + r8 * 4;
+      float* lo0 = S.hlo[it & 1] + kg0 * 32 + r8 * 4;
       const int nrg = ((cnt + 15) & ~15) / 8;
 #pragma unroll 1
-      for (int kb = pw; kb * 4 < kgroups; kb += 4) {
-        const int kg = kb * 4 + kq;
-#pragma unroll 4
-        for (int rg = 0; rg < nrg; ++rg) {
-          const float4 t = *reinterpret_cast<const float4*>(raw + rg * (FT_KMAX / 4 * 32) + kg * 32 + r8 * 4);
-          *reinterpret_cast<float4*>(lo + rg * (FT_KMAX / 4 * 32) + kg * 32 + r8 * 4) =
-              make_float4(tf32_lo(t.x), tf32_lo(t.y), tf32_lo(t.z), tf32_lo(t.w));
+      for (int j = 0; j < nkj; ++j) {
+        const float* raw = raw0 + j * (16 * 32);
+        float* lo = lo0 + j * (16 * 32);
+#pragma unroll 1
+        for (int rg = 0; rg < nrg; rg += 2) {  // nrg is even (N is a multiple of 16)
+          const float4 t0 = *reinterpret_cast<const float4*>(raw), t1 = *reinterpret_cast<const float4*>(raw + FT_KMAX / 4 * 32);
+          *reinterpret_cast<float4*>(lo) = make_float4(tf32_lo(t0.x), tf32_lo(t0.y), tf32_lo(t0.z), tf32_lo(t0.w));
+          *reinterpret_cast<float4*>(lo + FT_KMAX / 4 * 32) = make_float4(tf32_lo(t1.x), tf32_lo(t1.y), tf32_lo(t1.z), tf32_lo(t1.w));
+          raw += 2 * (FT_KMAX / 4 * 32);
+          lo += 2 * (FT_KMAX / 4 * 32);
         }
       }
     };
@@ -461,17 +481,23 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
         }
       }
       FTP_END(16, it)
-    } else if (warp == 13) {
-      // ================= x / Y stager ========================================================================
-      // lanes 0-7 = the edges of a stage: one bulk copy per (edge, input chunk of the slice); all lanes: Y elements
+    } else {
+      // ================= x / Y stagers (warps 13, 14, 15) =====================================================
+      const int sid = warp - 13;
       const int nseg = Spec::seg_count(slice);
-      int goff[FT_MAXSEG], slen[FT_MAXSEG], soff[FT_MAXSEG], rowbytes = 0;
+      int ppe = 0;  // 16-byte pieces per edge
+      for (int sgi = 0; sgi < nseg; ++sgi) ppe += Spec::seg_len(slice, sgi) / 4;
+      constexpr int PCL = (XROW / 4 + 31) / 32;  // pieces per lane and edge
+      int pg[PCL], ps[PCL];
 #pragma unroll
-      for (int s = 0; s < FT_MAXSEG; ++s) {
-        goff[s] = (s < nseg) ? Spec::seg_goff(slice, s) : 0;
-        slen[s] = (s < nseg) ? Spec::seg_len(slice, s) : 0;
-        soff[s] = rowbytes / 4;
-        rowbytes += slen[s] * 4;
+      for (int i = 0; i < PCL; ++i) {
+        int k = lane + 32 * i, sgi = 0, soff = 0;
+        pg[i] = -1; ps[i] = 0;
+        if (k < ppe) {
+          while (sgi + 1 < nseg && k >= Spec::seg_len(slice, sgi) / 4) { k -= Spec::seg_len(slice, sgi) / 4; soff += Spec::seg_len(slice, sgi); ++sgi; }
+          pg[i] = Spec::seg_goff(slice, sgi) + k * 4;
+          ps[i] = soff + k * 4;
+        }
       }
       constexpr int YPL = (FT_SUB * SD + 31) / 32;  // Y elements per lane and stage
       int ye[YPL], yj[YPL];
@@ -492,27 +518,31 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
           q0 = (lane < nxt.cnt) ? __ldg(a.src + nxt.t0 + lane) : 0;
           q1 = (32 + lane < nxt.cnt) ? __ldg(a.src + nxt.t0 + 32 + lane) : 0;
         }
-#pragma unroll
+#pragma unroll 1
         for (int sb = 0; sb < FT_TE / FT_SUB; ++sb) {
           const int e0 = sb * FT_SUB;
           if (e0 < cur.cnt) {
-            const uint32_t st = xs % NXS;
-            if (xs >= (uint32_t)NXS) FTP_WAIT(1, mbar_wait(&S.x_empty[st], ((xs / NXS) - 1) & 1))
-            float* stage = xring + (size_t)st * STAGE_FLOATS;
-            const int ne = (cur.cnt - e0 < FT_SUB) ? (cur.cnt - e0) : FT_SUB;
-            const int64_t row = __shfl_sync(0xffffffffu, (sb < 4) ? r0 : r1, (e0 + (lane & 7)) & 31);
-            if (lane == 0) mbar_expect_tx(&S.x_full[st], (uint32_t)(ne * rowbytes));
-            if (lane < ne) {
-              const float* xrow = a.x + row * Spec::D_IN;
+            if ((int)(xs % 3) == sid) {
+              const uint32_t st = xs % NXS;
+              if (xs >= (uint32_t)NXS) FTP_WAIT(1, mbar_wait(&S.x_empty[st], ((xs / NXS) - 1) & 1))
+              float* stage = xring + (size_t)st * STAGE_FLOATS;
+              const int ne = (cur.cnt - e0 < FT_SUB) ? (cur.cnt - e0) : FT_SUB;
+              const int64_t rsel = (sb < 4) ? r0 : r1;
+#pragma unroll 1
+              for (int e = 0; e < ne; ++e) {
+                const int64_t row = __shfl_sync(0xffffffffu, rsel, (e0 + e) & 31);
+                const float* xrow = a.x + row * Spec::D_IN;
+                float* drow = stage + e * XROW;
 #pragma unroll
-              for (int s = 0; s < FT_MAXSEG; ++s)
-                if (s < nseg) bulk_g2s(stage + lane * XROW + soff[s], xrow + goff[s], (uint32_t)(slen[s] * 4), &S.x_full[st]);
+                for (int i = 0; i < PCL; ++i)
+                  if (pg[i] >= 0) cp_async16(drow + ps[i], xrow + pg[i], 16u);
+              }
+              float* ys = stage + FT_SUB * XROW;  // [pair][S][2]
+#pragma unroll
+              for (int q = 0; q < YPL; ++q)
+                if (ye[q] < ne) ft_cp_async4(ys + ((ye[q] >> 1) * SD + yj[q]) * 2 + (ye[q] & 1), a.y + (cur.t0 + e0 + ye[q]) * SD + yj[q], 4u);
+              ft_cp_async_arrive(&S.x_full[st]);
             }
-            float* ys = stage + FT_SUB * XROW;  // [pair][S][2]
-#pragma unroll
-            for (int q = 0; q < YPL; ++q)
-              if (ye[q] < ne) ft_cp_async4(ys + ((ye[q] >> 1) * SD + yj[q]) * 2 + (ye[q] & 1), a.y + (cur.t0 + e0 + ye[q]) * SD + yj[q], 4u);
-            ft_cp_async_arrive(&S.x_full[st]);
             ++xs;
           }
         }
@@ -521,7 +551,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
         ++it;
       }
       cp_async_wait<0>();
-      FTP_END(24, it)
+      if (sid == 0) FTP_END(24, it)
     }
   }
   tc_fence_before();

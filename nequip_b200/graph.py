@@ -76,24 +76,6 @@ class GraphedEnergyForces:
         return self.model(d)
 
 
-class GraphedShardedEnergyForces(GraphedEnergyForces):
-    """The same replay for ONE RANK of a spatially decomposed frame (nequip_b200/parallel.py): the captured step
-    contains the per-layer NCCL halo exchanges, the energy all-reduce and the reverse exchange that returns the
-    ghost-position gradients to their owners (NCCL collectives are capturable).  ``forces`` are those of the
-    OWNED atoms ``[n_own, 3]``.  Every rank must construct and replay it collectively."""
-
-    def __init__(self, model, local: Dict[str, torch.Tensor], plan, halo, warmup: int = 3):
-        self.plan, self.halo = plan, halo
-        super().__init__(model, local, warmup=warmup)
-
-    def _run(self):
-        from . import parallel as P
-
-        d = dict(self.extra)
-        d.update(self.static)
-        e, f = P.sharded_energy_forces(self.model, d, self.plan, self.halo, reduce_forces="owner")
-        return {"total_energy": e, "forces": f}
-
     def matches(self, data: Dict[str, torch.Tensor]) -> bool:
         return all(k in data and tuple(data[k].shape) == s for k, s in self.shapes.items())
 
@@ -132,3 +114,22 @@ class GraphedShardedEnergyForces(GraphedEnergyForces):
         self._verify_previous()
         if int(self.sorted_flag.item()) != 1:
             raise RuntimeError("GraphedEnergyForces: edge_index is not grouped by destination; use the eager model call")
+
+
+class GraphedShardedEnergyForces(GraphedEnergyForces):
+    """The same replay for ONE RANK of a spatially decomposed frame (nequip_b200/parallel.py): the captured step
+    contains the per-layer NCCL halo exchanges, the energy all-reduce and the reverse exchange that returns the
+    ghost-position gradients to their owners (NCCL collectives are capturable).  ``forces`` are those of the
+    OWNED atoms ``[n_own, 3]``.  Every rank must construct and replay it collectively."""
+
+    def __init__(self, model, local: Dict[str, torch.Tensor], plan, halo, warmup: int = 3):
+        self.plan, self.halo = plan, halo
+        super().__init__(model, local, warmup=warmup)
+
+    def _run(self):
+        from . import parallel as P
+
+        d = dict(self.extra)
+        d.update(self.static)
+        e, f = P.sharded_energy_forces(self.model, d, self.plan, self.halo, reduce_forces="owner")
+        return {"total_energy": e, "forces": f}

@@ -87,6 +87,7 @@ class B200TensorProductScatter(_Base):
         self._sig = TPSignature(Irreps(feature_irreps_in), Irreps(irreps_edge_attr), Irreps(irreps_mid), list(instructions))
         self.weight_numel = self._sig.weight_numel
         self._plan_obj = None
+        self._key = None
 
     @property
     def _plan(self):
@@ -95,10 +96,21 @@ class B200TensorProductScatter(_Base):
             self._plan_obj = ops.get_plan(s.irreps_in1, s.irreps_in2, s.irreps_out, s.instructions, self._gen_options)
         return self._plan_obj
 
+    @property
+    def _plan_key(self) -> str:
+        if self._key is None:
+            from .. import torch_ops
+
+            self._key = torch_ops.register_plan(self._plan)
+        return self._key
+
     def forward(self, x, edge_attr, edge_weight, edge_dst, edge_src):
+        # one opaque ``torch.ops.nequip_b200.tp_scatter`` node (fake kernel + autograd of any order registered in
+        # nequip_b200/torch_ops.py): traceable by make_fx / torch.compile / torch.export, usable in training.
         # explicit cast to account for AMP (as the OpenEquivariance subclass does)
         dt = self.model_dtype
-        return ops.tp_scatter(self._plan, x.to(dt), edge_attr.to(dt), edge_weight.to(dt), edge_dst, edge_src)
+        return torch.ops.nequip_b200.tp_scatter(x.to(dt), edge_attr.to(dt), edge_weight.to(dt), edge_dst, edge_src,
+                                                self._plan_key)
 
 
 def _factory(old):
@@ -156,5 +168,5 @@ if _HAVE_NEQUIP:  # pragma: no cover - exercised only where nequip is installed
         persistent=False,
         private=False,
         unsupported_devices=["cpu"],
-        supported_compile_modes=[],
+        supported_compile_modes=["compile", "aotinductor"],  # opaque torch.library op with a fake kernel
     )(classmethod(_enable))

@@ -13,6 +13,7 @@ library raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
@@ -213,23 +214,7 @@ class _TPScatterFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
         x, y, w, edge_src = ctx.saved_tensors
-        plan, csr = ctx.plan, ctx.csr
-        L = _capi.lib()
-        N, E = x.shape[0], edge_src.numel()
-        need_x = ctx.needs_input_grad[0]
-        gx = torch.zeros_like(x) if need_x else None
-        gy = torch.zeros_like(y)
-        gw = torch.empty_like(w)
-        if N > 0 and E > 0:
-            gout = gout.contiguous()
-            _capi.check(
-                L.nqb_tp_scatter_bwd(plan.handle, _DT[x.dtype], _ptr(x), _ptr(y), _ptr(w), _ptr(csr.row_ptr),
-                                     _ptr(csr.perm), _ptr(edge_src), _ptr(gout), N, E, _ptr(gx), _ptr(gy), _ptr(gw),
-                                     _stream()),
-                "nqb_tp_scatter_bwd",
-            )
-        elif E == 0:
-            gw.zero_()
+        gx, gy, gw = tp_scatter_bwd_raw(ctx.plan, x, y, w, edge_src, ctx.csr, gout, need_x=ctx.needs_input_grad[0])
         return gx, (gy if ctx.needs_input_grad[1] else None), (gw if ctx.needs_input_grad[2] else None), None, None, None
 
 
@@ -331,23 +316,82 @@ def tp_fused_fwd(fw: FusedTPWeights, x: torch.Tensor, y: torch.Tensor, h: torch.
     return out, w
 
 
-def tp_scatter_bwd_raw(plan: TPPlan, x, y, w, edge_src, csr: EdgeCSR, gout, need_x: bool = True):
+_DETERMINISTIC = os.environ.get("NQB_DETERMINISTIC", "0") not in ("", "0")
+
+
+def set_deterministic(on: bool = True) -> None:
+    """Bitwise-repeatable backward of the fused TP+scatter (also implied by ``torch.use_deterministic_algorithms``):
+    grad_x goes through a per-edge buffer and a source-sorted segmented sum, grad_Y through one slice per writer,
+    instead of ``red.global.add`` in arrival order (the default, like the reference's OpenEquivariance back-end)."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = bool(on)
+
+
+def deterministic() -> bool:
+    return _DETERMINISTIC or torch.are_deterministic_algorithms_enabled()
+
+
+class _SrcCSRCache:
+    """Source-sorted view of the edge list (the reference's edge_transpose_perm): one entry per thread."""
+
+    def __init__(self):
+        self._tls = threading.local()
+
+    def get(self, edge_src: torch.Tensor, num_nodes: int):
+        key = (edge_src.data_ptr(), edge_src.numel(), edge_src._version, num_nodes, edge_src.device)
+        ent = getattr(self._tls, "ent", None)
+        if ent is not None and ent[0] == key:
+            return ent[1], ent[2]
+        keys, perm = torch.sort(edge_src, stable=True)
+        seg = torch.empty(num_nodes + 1, dtype=torch.int64, device=edge_src.device)
+        _capi.check(_capi.lib().nqb_csr_from_sorted(_ptr(keys.contiguous()), edge_src.numel(), num_nodes, _ptr(seg), _stream()),
+                    "nqb_csr_from_sorted")
+        self._tls.ent = (key, perm.contiguous(), seg, edge_src)
+        return self._tls.ent[1], seg
+
+    def clear(self):
+        self._tls.ent = None
+
+
+src_csr_cache = _SrcCSRCache()
+
+
+def tp_scatter_bwd_raw(plan: TPPlan, x, y, w, edge_src, csr: EdgeCSR, gout, need_x: bool = True,
+                       force_deterministic: Optional[bool] = None):
     """Backward kernels of the fused TP+scatter on raw tensors: (grad_x or None, grad_y, grad_w)."""
     L = _capi.lib()
     N, E = x.shape[0], edge_src.numel()
-    gx = torch.zeros_like(x) if need_x else None
-    gy = torch.zeros_like(y)
+    det = deterministic() if force_deterministic is None else bool(force_deterministic)
     gw = torch.empty_like(w)
-    if N > 0 and E > 0:
-        gout = gout.contiguous()
-        _capi.check(
-            L.nqb_tp_scatter_bwd(plan.handle, _DT[x.dtype], _ptr(x), _ptr(y), _ptr(w), _ptr(csr.row_ptr),
-                                 _ptr(csr.perm), _ptr(edge_src), _ptr(gout), N, E, _ptr(gx), _ptr(gy), _ptr(gw),
-                                 _stream()),
-            "nqb_tp_scatter_bwd",
-        )
-    elif E == 0:
+    if N == 0 or E == 0:
         gw.zero_()
+        return (torch.zeros_like(x) if need_x else None), torch.zeros_like(y), gw
+    gout = gout.contiguous()
+    dt = _DT[x.dtype]
+    if not det:
+        gx = torch.zeros_like(x) if need_x else None
+        gy = torch.zeros_like(y)
+        _capi.check(L.nqb_tp_scatter_bwd(plan.handle, dt, _ptr(x), _ptr(y), _ptr(w), _ptr(csr.row_ptr), _ptr(csr.perm),
+                                         _ptr(edge_src), _ptr(gout), N, E, _ptr(gx), _ptr(gy), _ptr(gw), 0, _stream()),
+                    "nqb_tp_scatter_bwd")
+        return gx, gy, gw
+    ns = int(L.nqb_tp_scatter_gy_slices(plan.handle, dt))
+    if ns <= 0:
+        raise RuntimeError("nequip_b200: this kernel library has no deterministic backward")
+    gxe = torch.empty((E, x.shape[1]), dtype=x.dtype, device=x.device) if need_x else None
+    gys = torch.zeros((ns, E, y.shape[1]), dtype=y.dtype, device=y.device)
+    _capi.check(L.nqb_tp_scatter_bwd(plan.handle, dt, _ptr(x), _ptr(y), _ptr(w), _ptr(csr.row_ptr), _ptr(csr.perm),
+                                     _ptr(edge_src), _ptr(gout), N, E, _ptr(gxe), _ptr(gys), _ptr(gw), 1, _stream()),
+                "nqb_tp_scatter_bwd")
+    gx = None
+    if need_x:
+        perm_t, seg_t = src_csr_cache.get(edge_src, N)
+        gx = torch.empty_like(x)
+        _capi.check(L.nqb_segment_sum(dt, _ptr(gxe), x.shape[1], _ptr(perm_t), _ptr(seg_t), N, _ptr(gx), _stream()),
+                    "nqb_segment_sum")
+    gy = gys[0]
+    for q in range(1, ns):  # fixed order
+        gy = gy + gys[q]
     return gx, gy, gw
 
 

@@ -66,7 +66,7 @@ def main():
             def bwd():
                 ops._capi.check(L.nqb_tp_scatter_bwd(tps._plan.handle, 0, x.data_ptr(), y.data_ptr(), w.data_ptr(),
                                                      csr.row_ptr.data_ptr(), 0, src_idx.data_ptr(), gout.data_ptr(), N, E,
-                                                     0 if gx is None else gx.data_ptr(), gy.data_ptr(), gw.data_ptr(),
+                                                     0 if gx is None else gx.data_ptr(), gy.data_ptr(), gw.data_ptr(), 0,
                                                      torch.cuda.current_stream().cuda_stream), "bwd")
 
             ms = timeit(bwd, args.reps)

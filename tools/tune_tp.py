@@ -85,7 +85,7 @@ def main():
             def bwd():
                 ops._capi.check(L.nqb_tp_scatter_bwd(plan.handle, 0, x.data_ptr(), y.data_ptr(), w.data_ptr(), csr.row_ptr.data_ptr(),
                                                      0, src.data_ptr(), gout.data_ptr(), N, E, gx.data_ptr(), gy.data_ptr(),
-                                                     gw.data_ptr(), st), "bwd")
+                                                     gw.data_ptr(), 0, st), "bwd")
 
             tf, tb = timeit(fwd), timeit(bwd)
             if ref_out is None:
