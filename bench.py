@@ -305,7 +305,7 @@ def kernel_rooflines(model, resident, n_atoms, n_edges, reps, ms_step, dev):
             gh = torch.empty(E, K, device=dev)
             flops3 = 3 * 2.0 * E * K * W
             tc = conv._tc_cache[1] if conv._tc_cache else None
-            fused = tc["fused"] if (tc and conv.use_fused_radial_tp) else None
+            fused = tc["fused"] if (tc and tc["fused"] is not None and (conv.use_fused_radial_tp is True or conv._fused_choice)) else None
             if fused is not None:
                 ms = _time_cuda(lambda: ops.tp_fused_fwd(fused.fw, x, y, h, src, csr, want_w=True), reps)
                 alg = 4 * (N * sig.d_in + E * sig.s_dim + E * K + N * sig.d_out + E * W) + 16 * E + 8 * K * W
@@ -593,6 +593,10 @@ def main():
                                 else f"dp{world} over frames (one {n_atoms}-atom frame per GPU)"),
                 "launch": ("one CUDA-graph replay per step (nequip_b200/graph.py)" if graphed is not None
                            else "eager launches"),
+                "radial_tp_path": [
+                    {"layer": i, "choice": ("fused (nqb_tp_fused_fwd)" if l.conv._fused_choice else "k_gemm3x + tp_fwd*"),
+                     **{k: round(v, 4) for k, v in (getattr(l.conv, "fused_timing_ms", None) or {}).items()}}
+                    for i, l in enumerate(model.layers)],
                 "l2_policy": "inputs larger than L2 (edge weights of one layer: %.2f GB)" % (
                     n_edges * max(l.conv.tp_scatter.weight_numel for l in model.layers) * 4 / 1e9),
             },

@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 18
+CODEGEN_VERSION = 19
 
 
 # ---------------------------------------------------------------------------
@@ -873,7 +873,9 @@ class TPGenerator:
             for p in grp:
                 cols += [p.woff + u for u in range(mul)]
             cols += [-1] * (128 - mul * len(grp))
-        cost = [sum(self.path_cost(p) for p in grp) * (mul // 32) for grp in slices]
+        # per-tile time of a slice = a path-independent part (h tile, weights MMA, staging: ~5.3 k cycles measured)
+        # + the consumer arithmetic (~13 cycles per cost unit): profiles/r02_fused_v2b.txt
+        cost = [400 + sum(self.path_cost(p) for p in grp) * (mul // 32) for grp in slices]
         return dict(mul=mul, pps=pps, slices=slices, segs=segs, xrow=xrow, nxs=int(nxs), cols=cols, cost=cost)
 
     def _emit_fused_path(self, em: _Emitter, p: Path, xs_off: int, mul: int):

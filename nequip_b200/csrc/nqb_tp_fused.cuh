@@ -395,11 +395,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
         float* dst = dst0 + j * (16 * 32);
         const float* src = src0 + j * 64;
 #pragma unroll 1
-        for (int rg = 0; rg < nrg; ++rg) {
-          const bool in = rg * 8 + r8 < cnt;
-          cp_async16(dst, in ? src : a.h, in ? 16u : 0u);
-          dst += FT_KMAX / 4 * 32;
-          src += rstep;
+        for (int rg = 0; rg < nrg; rg += 2) {  // nrg is even (N is a multiple of 16)
+          const bool in0 = rg * 8 + r8 < cnt, in1 = rg * 8 + 8 + r8 < cnt;
+          cp_async16(dst, in0 ? src : a.h, in0 ? 16u : 0u);
+          cp_async16(dst + FT_KMAX / 4 * 32, in1 ? (src + rstep) : a.h, in1 ? 16u : 0u);
+          dst += 2 * (FT_KMAX / 4 * 32);
+          src += 2 * rstep;
         }
       }
     };
@@ -528,14 +529,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tp_fused_fwd_kernel(const Fused
               float* stage = xring + (size_t)st * STAGE_FLOATS;
               const int ne = (cur.cnt - e0 < FT_SUB) ? (cur.cnt - e0) : FT_SUB;
               const int64_t rsel = (sb < 4) ? r0 : r1;
+              // four edges per iteration: the shuffle -> address -> cp.async chains of the edges interleave
 #pragma unroll 1
-              for (int e = 0; e < ne; ++e) {
-                const int64_t row = __shfl_sync(0xffffffffu, rsel, (e0 + e) & 31);
-                const float* xrow = a.x + row * Spec::D_IN;
-                float* drow = stage + e * XROW;
+              for (int eb = 0; eb < ne; eb += 4) {
+                const float* xrow[4];
 #pragma unroll
-                for (int i = 0; i < PCL; ++i)
-                  if (pg[i] >= 0) cp_async16(drow + ps[i], xrow + pg[i], 16u);
+                for (int q = 0; q < 4; ++q) xrow[q] = a.x + __shfl_sync(0xffffffffu, rsel, (e0 + eb + q) & 31) * Spec::D_IN;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (eb + q < ne) {
+                    float* drow = stage + (eb + q) * XROW;
+#pragma unroll
+                    for (int i = 0; i < PCL; ++i)
+                      if (pg[i] >= 0) cp_async16(drow + ps[i], xrow[q] + pg[i], 16u);
+                  }
+                }
               }
               float* ys = stage + FT_SUB * XROW;  // [pair][S][2]
 #pragma unroll

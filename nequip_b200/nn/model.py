@@ -320,7 +320,8 @@ class InteractionBlock(torch.nn.Module):
         self.linear_2 = Linear(irreps_mid.simplify(), fout, layout)
         self.sc = SelfConnection(fin, num_node_attrs, fout, layout) if use_sc else None
         self.use_tensor_cores = True
-        self.use_fused_radial_tp = True  # SURVEY 8f-1 kernel when the signature has one (mul % 32 == 0, K <= 128)
+        self.use_fused_radial_tp = "auto"  # SURVEY 8f-1 kernel (mul % 32 == 0, K <= 128): True / False / "auto" (timed once)
+        self._fused_choice = None
         self.strict_fast_path = False
         self._tc_cache = None
 
@@ -328,6 +329,38 @@ class InteractionBlock(torch.nn.Module):
         """Radial MLP, plain torch.mm formulation of the reference (mlp.py:262-268) -- the path for trainable
         weights, float64 and unusual shapes; frozen float32 ir_mul models use ``_tensor_core_blocks``."""
         return self.edge_mlp(edge_embedding)
+
+    def _use_fused(self, tc, edge_embedding, x, edge_attrs, edge_index) -> bool:
+        """``use_fused_radial_tp``: True / False, or "auto" (default) = time the fused kernel against the unfused pair
+        (grouped GEMM + TP kernel) ONCE per layer on the first real call and keep the faster one.  The fused kernel
+        never materialises the [E, W] weights in the forward pass, but its path-parallel decomposition gives up the
+        sharing of the x_i Y_j products between paths: which one wins depends on the signature (measurements in
+        DESIGN.md section 4.7)."""
+        mode = self.use_fused_radial_tp
+        if mode is True or mode is False:
+            return mode
+        if self._fused_choice is None:
+            if torch.cuda.is_current_stream_capturing() or tc["mlp"] is None:
+                return False
+            with torch.no_grad():
+                def t(fn):
+                    fn()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(2):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    return e0.elapsed_time(e1) / 2
+
+                xd, yd, ed = x.detach(), edge_attrs.detach(), edge_embedding.detach()
+                tf = t(lambda: tc["fused"](ed, xd, yd, edge_index[0], edge_index[1]))
+                tu = t(lambda: self.tp_scatter(x=xd, edge_attr=yd, edge_weight=tc["mlp"](ed), edge_dst=edge_index[0],
+                                               edge_src=edge_index[1]))
+            self._fused_choice = bool(tf < tu)
+            self.fused_timing_ms = {"fused": tf, "unfused": tu}
+        return self._fused_choice
 
     def _note_fallback(self, reason: str):
         """The library (torch.matmul / cuBLAS) formulation is about to run instead of the tcgen05 blocks: say so
@@ -361,7 +394,7 @@ class InteractionBlock(torch.nn.Module):
             x = tc["lin1"](x)  # 1/sqrt(avg_num_neighbors) folded into the prepared weights
             if halo is not None and not self.is_first_layer:
                 x = halo(x)
-            if tc["fused"] is not None and self.use_fused_radial_tp:
+            if tc["fused"] is not None and self._use_fused(tc, edge_embedding, x, edge_attrs, edge_index):
                 # one kernel: last radial layer (tcgen05, weights resident in tensor memory) -> TP -> scatter
                 y = tc["fused"](edge_embedding, x, edge_attrs, edge_index[0], edge_index[1])
                 if y is not None:

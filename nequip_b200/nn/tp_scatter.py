@@ -25,6 +25,7 @@ from typing import Optional
 import torch
 
 from .. import ops
+from .. import torch_ops  # registers torch.ops.nequip_b200.* (no native code is loaded by the import)
 from ..codegen import GenOptions
 from ..irreps import Irreps
 
@@ -99,8 +100,6 @@ class B200TensorProductScatter(_Base):
     @property
     def _plan_key(self) -> str:
         if self._key is None:
-            from .. import torch_ops
-
             self._key = torch_ops.register_plan(self._plan)
         return self._key
 

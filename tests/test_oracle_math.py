@@ -173,3 +173,56 @@ def test_oracle_model_finite_difference_forces():
             d["pos"] = p
             es.append(om.energy(m.state_dict(), m.config, d, torch.float64)[0].item())
         assert -(es[0] - es[1]) / (2 * eps) == pytest.approx(f[i, c].item(), rel=1e-6, abs=1e-9)
+
+
+def test_su2_clebsch_gordan_against_sympy():
+    """Independent published implementation (sympy.physics.quantum.cg.CG, Condon-Shortley convention): the oracle's
+    Racah-formula SU(2) coefficients, which the real Wigner-3j tensors are built from, agree for every l <= 3 triple."""
+    sympy = pytest.importorskip("sympy")
+    from sympy.physics.quantum.cg import CG
+
+    for l1 in range(4):
+        for l2 in range(4):
+            for l3 in range(abs(l1 - l2), min(3, l1 + l2) + 1):
+                ours = wigner.su2_cg(l1, l2, l3)
+                for m1 in range(-l1, l1 + 1):
+                    for m2 in range(-l2, l2 + 1):
+                        m3 = m1 + m2
+                        if abs(m3) > l3:
+                            continue
+                        ref = float(CG(l1, m1, l2, m2, l3, m3).doit())
+                        assert abs(float(ours[l1 + m1, l2 + m2, l3 + m3]) - ref) < 1e-12, (l1, l2, l3, m1, m2)
+
+
+def test_real_sh_against_scipy_complex_harmonics():
+    """Independent implementation (scipy.special sph_harm): the oracle's real harmonics are, up to the e3nn
+    convention's fixed real-basis change (m < 0 sine-like, m > 0 cosine-like, axis order y, z, x) and the
+    'component' normalisation sqrt(4 pi), the standard real spherical harmonics."""
+    scipy_special = pytest.importorskip("scipy.special")
+    sph = getattr(scipy_special, "sph_harm_y", None)
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(50, 3, generator=g, dtype=torch.float64)
+    v = v / v.norm(dim=1, keepdim=True)
+    Y = osh.spherical_harmonics(3, v, normalize=True).numpy()
+    # e3nn convention: the "z" axis of the standard harmonics is the y component, (x, y) -> (z, x)
+    x, y, z = v[:, 2].numpy(), v[:, 0].numpy(), v[:, 1].numpy()
+    theta, phi = np.arccos(np.clip(z, -1, 1)), np.arctan2(y, x)
+    off = 0
+    for l in range(4):
+        for m in range(-l, l + 1):
+            if sph is not None:
+                c = sph(l, abs(m), theta, phi)
+            else:
+                c = scipy_special.sph_harm(abs(m), l, phi, theta)
+            if m == 0:
+                std = c.real
+            elif m > 0:
+                std = np.sqrt(2) * (-1) ** m * c.real
+            else:
+                std = np.sqrt(2) * (-1) ** m * c.imag
+            ours = Y[:, off + l + m] / np.sqrt(4 * np.pi)
+            # sign conventions per (l, m) are fixed constants: compare up to that sign, and require it to be uniform
+            s = np.sign(np.sum(ours * std))
+            assert s != 0
+            np.testing.assert_allclose(ours, s * std, atol=1e-12, err_msg=f"l={l} m={m}")
+        off += 2 * l + 1

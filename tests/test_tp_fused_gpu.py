@@ -91,6 +91,8 @@ def test_model_with_fused_kernel_matches_oracle_and_unfused(name, kind, mk):
                               avg_num_neighbors=meta["avg_num_neighbors"], strict_fast_path=True, **mk).cuda()
     for p in model.parameters():
         p.requires_grad_(False)
+    for l in model.layers:
+        l.conv.use_fused_radial_tp = True  # (the default "auto" times both paths once and keeps the faster)
     dev = D.to_device(sysd, "cuda")
     out = model(dev)
     used = [l.conv._tc_cache[1]["fused"] is not None for l in model.layers]
