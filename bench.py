@@ -12,11 +12,16 @@ r_max 5 A -- on a synthetic ~10k-atom Li3PO4-like periodic box (10 648 atoms, ~5
 `value`  : device-resident inputs, CUDA-event timed, max over ranks.
 `e2e`    : the same step through NequIPEnergyModel.forward with HOST (pinned) inputs: H2D of
            pos/edge_index/shifts/types/cell and D2H of forces+energy inside the timed region.
-`roofline`: the fused TP+scatter forward kernel of the largest layer, timed alone with CUDA
-           events on the launching stream, algorithmic bytes / duration vs the measured HBM peak.
-N > 1: one process per GPU (torchrun), each rank owns an independent frame of the same size
-(data-parallel over frames, as the reference's DDP does; "weak"), one NCCL all-reduce of the
-per-frame energies per step.
+`e2e_device_neighbor_list`: as `e2e`, but only positions travel and the neighbour list is built on the GPU.
+`roofline`: every hot kernel class of every layer timed ALONE (CUDA events on the launching stream, step-sized
+           inputs > L2); the class with the largest share of the step is the headline, the rest is under
+           `roofline.by_kernel` (HBM fraction of the measured copy peak; for the tcgen05 GEMMs also the 3xTF32
+           issue rate against half the measured bf16 cuBLAS rate, and the ncu tensor-pipe activity).
+N > 1 (default): ONE frame partitioned by atoms into N bricks with halo (ghost) atoms -- the north_star
+partition: per-layer NCCL halo exchange of ghost features, energy all-reduce, ghost-force reduction to the
+owners; the whole sharded step is one CUDA-graph replay per rank.  `--scaling weak` (default) grows the frame
+with N (N x 10 648 atoms, box elongated along x), `--scaling strong` splits the 10 648-atom frame.
+`--decomp frames` keeps the round-1 mode (one independent frame per GPU, the reference's DDP axis).
 """
 import argparse
 import json
@@ -511,6 +516,24 @@ def main():
         e_host.copy_(out["total_energy"].view(-1), non_blocking=True)
         return out
 
+    def step_e2e_device_nl():
+        """Host positions in, forces out, with the neighbour list built ON THE DEVICE (ops.neighbor_list):
+        the host ships 24 bytes per atom instead of ~40 bytes per edge."""
+        pos_d = host["pos"].to(dev, non_blocking=True)
+        nl = ops.neighbor_list(pos_d, sysd["cell"], True, R_MAX)
+        if graphed is not None and tuple(nl["edge_index"].shape) == tuple(graphed.static["edge_index"].shape):
+            graphed.static["pos"].copy_(pos_d)
+            graphed.static["edge_index"].copy_(nl["edge_index"])
+            graphed.static["edge_cell_shift"].copy_(nl["edge_cell_shift"])
+            out = graphed.replay()
+        else:
+            d = dict(resident)
+            d.update(pos=pos_d, edge_index=nl["edge_index"], edge_cell_shift=nl["edge_cell_shift"])
+            out = model(d)
+        f_host.copy_(out["forces"], non_blocking=True)
+        e_host.copy_(out["total_energy"].view(-1), non_blocking=True)
+        return out
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -551,6 +574,9 @@ def main():
         sampler.start()
     ms_res, launches = timed(step_resident, args.steps, args.warmup)
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    ms_e2e_nl = None
+    if world == 1 and "cell" in sysd:
+        ms_e2e_nl, _ = timed(step_e2e_device_nl, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
     if graphed is not None:
         graphed.check_sorted()  # the in-graph "edges grouped by destination" flag of the last replay
@@ -602,6 +628,10 @@ def main():
             },
             "e2e": {"value": total_atoms / (ms_e2e * 1e-3), "unit": "atom-steps/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_device_neighbor_list": (None if ms_e2e_nl is None else {
+                "value": total_atoms / (ms_e2e_nl * 1e-3), "unit": "atom-steps/s", "ms_per_step": ms_e2e_nl,
+                "h2d_bytes_per_step": int(host["pos"].numel() * 8), "d2h_bytes_per_step": d2h,
+                "note": "positions in, forces out; neighbour list (cell list) built on the GPU inside the timed region"}),
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

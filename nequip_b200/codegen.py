@@ -47,7 +47,7 @@ from typing import Dict, List, Tuple
 from . import cg
 from .irreps import Irreps
 
-CODEGEN_VERSION = 19
+CODEGEN_VERSION = 21
 
 
 # ---------------------------------------------------------------------------
@@ -174,6 +174,8 @@ class GenOptions:
     fwd_ring: bool = True  # forward v2: one CTA per node, weight rows streamed through a cp.async.bulk smem ring
     ring_stages: int = 4
     bwd_ring: bool = True  # backward v2 (same weight ring)
+    split_groups: bool = False  # register (v1) kernels: one launch per path group instead of one launch for all --
+    #                              every SM then executes ONE group's (large, fully unrolled) body at a time
     fused_prof: bool = False  # per-role stall counters in the fused radial-MLP + TP kernel (tools/bench_fused.py --prof)
     layout: str = "mul_ir"  # node-feature layout of x / out: "mul_ir" (the reference's, e3nn) or
     #                         "ir_mul" (channel-contiguous: every chunk is [2l+1, mul]; all node-feature
@@ -182,7 +184,7 @@ class GenOptions:
     def tag(self) -> str:
         return (f"w{self.nwarp}_a{self.acc_cap}_b{self.acc_cap_bwd}_p{int(self.prefetch)}{int(self.idx_ahead)}"
                 f"_m{self.min_blocks_fwd}{self.min_blocks_bwd}_r{int(self.red_v2)}_{self.layout}_g{int(self.fwd_ring)}{self.ring_stages}{int(self.bwd_ring)}"
-                + ("_fp" if self.fused_prof else ""))
+                + ("_fp" if self.fused_prof else "") + ("_sg" if self.split_groups else ""))
 
 
 # ---------------------------------------------------------------------------
@@ -967,6 +969,15 @@ class TPGenerator:
         em.end("};")
         return True
 
+    def _emit_v1_launch(self, em: _Emitter, ng: str, tname: str, kernel: str, args: str):
+        """Launch of a register (v1) kernel: all path groups in one grid, or one launch per group (split_groups)."""
+        if self.opts.split_groups:
+            em(f"for (int g_ = 0; g_ < {ng}; ++g_) {{ dim3 grid_((unsigned)((N + NWARP - 1) / NWARP), VT<{tname}>::CB); "
+               f"{kernel}<<<grid_, block, 0, st>>>({args}, g_); }}")
+        else:
+            em(f"{{ dim3 grid_((unsigned)((N + NWARP - 1) / NWARP), {ng} * VT<{tname}>::CB); "
+               f"{kernel}<<<grid_, block, 0, st>>>({args}, 0); }}")
+
     # -- translation unit ----------------------------------------------------------------
     def source(self) -> str:
         sig = self.sig
@@ -1006,7 +1017,10 @@ class TPGenerator:
         # signatures (3-4 paths: first/last layer) keep the register-resident v1 kernel (measured)
         # (and only while the ring fits: a signature whose ring would exceed ~200 KB keeps the register kernel)
         ring_bytes = self.opts.ring_stages * self.geometry(2)[1] * sig.weight_numel * 4 + 2 * self.opts.ring_stages * 8 + 256 * 16
-        ring_fits = ring_bytes <= 200 * 1024
+        # ... and only when one edge fills the warp (mul >= 64 -> EPW == 1): with two or more edges per warp iteration the
+        # ring is EPW x larger per CTA (70-140 KB for the l_max = 3 layers -> 1-3 CTAs per SM) and the register kernels
+        # are up to 3.4x faster (a-Si layer 3: 5.8 / 14.0 ms against 17.2 / 49.3 ms, profiles/r02_tune_tp_lmax3_ring_vs_register.jsonl)
+        ring_fits = ring_bytes <= 200 * 1024 and self.geometry(2)[1] == 1
         self.use_ring = bool(self.opts.fwd_ring and sig.weight_numel % 4 == 0 and len(self.fwd_groups) >= 2 and ring_fits)
         if self.use_ring:
             em(f"constexpr int F2_STAGES = {self.opts.ring_stages};")
@@ -1032,13 +1046,13 @@ class TPGenerator:
             f"template <typename T> __global__ void __launch_bounds__(32 * NWARP{mbf}) tp_fwd_kernel("
             "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
             "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
-            "const int64_t* __restrict__ src, int64_t N, T* __restrict__ out)"
+            "const int64_t* __restrict__ src, int64_t N, T* __restrict__ out, int grp0)"
         )
         em("constexpr int CB = VT<T>::CB, LPE = VT<T>::LPE, CPT = VT<T>::CPT;")
         em("const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
         em("const int64_t n = (int64_t)blockIdx.x * NWARP + warp;")
         em("if (n >= N) return;")
-        em("const int grp = blockIdx.y / CB, cb = blockIdx.y % CB;")
+        em("const int grp = grp0 + blockIdx.y / CB, cb = blockIdx.y % CB;")
         em("const int sub = lane / LPE, cl = lane % LPE;")
         em("const int ch0 = (cb * LPE + cl) * CPT;")
         em("const int64_t beg = row_ptr[n], end = row_ptr[n + 1];")
@@ -1048,7 +1062,7 @@ class TPGenerator:
         em("default: break;")
         em.end()
         if unwritten:
-            em.block("if (blockIdx.y == 0)")
+            em.block("if (grp == 0 && cb == 0)")
             for io in unwritten:
                 mul, ir = sig.irreps_out[io]
                 ooff = sig.irreps_out.offsets()[io]
@@ -1102,13 +1116,13 @@ class TPGenerator:
             "const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ w, "
             "const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ perm, "
             "const int64_t* __restrict__ src, const T* __restrict__ gout, int64_t N, "
-            "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw, int det, int64_t gy_slice)"
+            "T* __restrict__ gx, T* __restrict__ gy, T* __restrict__ gw, int det, int64_t gy_slice, int grp0)"
         )
         em("constexpr int CB = VT<T>::CB, LPE = VT<T>::LPE, CPT = VT<T>::CPT;")
         em("const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
         em("const int64_t n = (int64_t)blockIdx.x * NWARP + warp;")
         em("if (n >= N) return;")
-        em("const int grp = blockIdx.y / CB, cb = blockIdx.y % CB;")
+        em("const int grp = grp0 + blockIdx.y / CB, cb = blockIdx.y % CB;")
         em("const int sub = lane / LPE, cl = lane % LPE;")
         em("const int ch0 = (cb * LPE + cl) * CPT;")
         em("const int64_t beg = row_ptr[n], end = row_ptr[n + 1];")
@@ -1116,7 +1130,7 @@ class TPGenerator:
         for gid in range(len(self.bwd_groups)):
             em(
                 f"case {gid}: bwd_g{gid}<T, WANT_GX>(x, y, w, perm, src, gout, n, beg, end, ch0, sub, cl, "
-                "gx, gy + (int64_t)blockIdx.y * gy_slice, gw, det != 0); break;"
+                "gx, gy + (int64_t)(grp * CB + cb) * gy_slice, gw, det != 0); break;"
             )
         em("default: break;")
         em.end()
@@ -1188,12 +1202,12 @@ class TPGenerator:
             em("dim3 grid2((unsigned)N, VT<float>::CB), block2(32 * NGF);")
             em("tp_fwd2_kernel<<<grid2, block2, F2_SMEM, st>>>((const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, N, (float*)out);")
         else:
-            em("dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGF * VT<float>::CB);")
-            em("tp_fwd_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, N, (float*)out);")
+            self._emit_v1_launch(em, "NGF", "float", "tp_fwd_kernel<float>",
+                                 "(const float*)x, (const float*)y, (const float*)w, row_ptr, perm, src, N, (float*)out")
         em.end()
         em.block("else")
-        em("dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGF * VT<double>::CB);")
-        em("tp_fwd_kernel<double><<<grid, block, 0, st>>>((const double*)x, (const double*)y, (const double*)w, row_ptr, perm, src, N, (double*)out);")
+        self._emit_v1_launch(em, "NGF", "double", "tp_fwd_kernel<double>",
+                             "(const double*)x, (const double*)y, (const double*)w, row_ptr, perm, src, N, (double*)out")
         em.end()
         em("return (int)cudaGetLastError();")
         em.end()
@@ -1227,13 +1241,16 @@ class TPGenerator:
             em.end()
         for dt, name in ((0, "float"), (1, "double")):
             em.block(f"if (dtype == {dt})")
-            em(f"dim3 grid((unsigned)((N + NWARP - 1) / NWARP), NGB * VT<{name}>::CB);")
             args = (
                 f"(const {name}*)x, (const {name}*)y, (const {name}*)w, row_ptr, perm, src, "
                 f"(const {name}*)gout, N, ({name}*)gx, ({name}*)gy, ({name}*)gw, det, gy_slice"
             )
-            em(f"if (gx) tp_bwd_kernel<{name}, true><<<grid, block, 0, st>>>({args});")
-            em(f"else tp_bwd_kernel<{name}, false><<<grid, block, 0, st>>>({args});")
+            em.block("if (gx)")
+            self._emit_v1_launch(em, "NGB", name, f"tp_bwd_kernel<{name}, true>", args)
+            em.end()
+            em.block("else")
+            self._emit_v1_launch(em, "NGB", name, f"tp_bwd_kernel<{name}, false>", args)
+            em.end()
             em.end()
         em("return (int)cudaGetLastError();")
         em.end()

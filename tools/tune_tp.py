@@ -19,6 +19,11 @@ VARIANTS = {
     "irmul_b16": GenOptions(layout="ir_mul", acc_cap_bwd=16),
     "irmul_b32": GenOptions(layout="ir_mul", acc_cap_bwd=32),
     "irmul_st6": GenOptions(layout="ir_mul", ring_stages=6),
+    "irmul_noring": GenOptions(layout="ir_mul", fwd_ring=False, bwd_ring=False),
+    "irmul_noring_split": GenOptions(layout="ir_mul", fwd_ring=False, bwd_ring=False, split_groups=True),
+    "irmul_noring_split_a16": GenOptions(layout="ir_mul", fwd_ring=False, bwd_ring=False, split_groups=True, acc_cap=16, acc_cap_bwd=16),
+    "irmul_noring_split_a64": GenOptions(layout="ir_mul", fwd_ring=False, bwd_ring=False, split_groups=True, acc_cap=64, acc_cap_bwd=64),
+    "irmul_ring_a16": GenOptions(layout="ir_mul", acc_cap=16, acc_cap_bwd=16),
 }
 # earlier sweeps (register prefetch, accumulator caps, warps per CTA, red.v2): profiles/r01_tune_tp_variants_*.jsonl
 
