@@ -56,8 +56,12 @@ class _GemmLinearFn(torch.autograd.Function):
 class IrrepsLinearGemm:
     """``o3.Linear`` in ir_mul layout from a ``nequip_b200.nn.model.Linear`` module's weights."""
 
-    def __init__(self, lin, device, extra_scale: float = 1.0):
+    def __init__(self, lin, device, extra_scale: float = 1.0, row_scaled: bool = False):
+        """``row_scaled``: every problem multiplies its output rows by row 0 of the ``rowscale`` matrix given at call
+        time (the per-atom-type AvgNumNeighborsNorm factor, nequip/nn/norm.py:48-68)."""
         fin, fout = lin.irreps_in, lin.irreps_out
+        rs = 0 if row_scaled else -1
+        self.row_scaled = row_scaled
         in_off, out_off = fin.offsets(), fout.offsets()
         self.d_in, self.d_out = fin.dim, fout.dim
         fwd: List[ops.GemmProblem] = []
@@ -73,9 +77,9 @@ class IrrepsLinearGemm:
             for c in range(ir.dim):
                 a_off, c_off = in_off[i] + c * mi, out_off[o] + c * mo
                 fwd.append(ops.GemmProblem(a_off, self.d_in, c_off, self.d_out, W, scale=pw * extra_scale,
-                                           atomic=n_out[o] > 1))
+                                           atomic=n_out[o] > 1, rs_off=rs))
                 bwd.append(ops.GemmProblem(c_off, self.d_out, a_off, self.d_in, W, scale=pw * extra_scale, transposed=True,
-                                           atomic=n_in[i] > 1))
+                                           atomic=n_in[i] > 1, rs_off=rs))
         self.zero_out = any(n != 1 for n in n_out.values())
         self.zero_in = any(n != 1 for n in n_in.values())
         self.fwd = ops.GroupedGemm(fwd, device)
@@ -86,9 +90,11 @@ class IrrepsLinearGemm:
         muls = [m for m, _ in lin.irreps_in] + [m for m, _ in lin.irreps_out]
         return lin.layout == "ir_mul" and all(m % 4 == 0 for m in muls) and lin.weight.dtype == torch.float32
 
-    def __call__(self, x):
+    def __call__(self, x, rowscale=None):
+        if self.row_scaled != (rowscale is not None):
+            raise ValueError("IrrepsLinearGemm: rowscale must be given exactly when built with row_scaled=True")
         return _GemmLinearFn.apply(x.contiguous(), self.fwd, self.bwd, self.d_out, self.zero_out, self.d_in, self.zero_in,
-                                   None, None)
+                                   rowscale, None)
 
 
 class SelfConnectionGemm:

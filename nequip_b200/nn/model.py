@@ -309,7 +309,11 @@ class InteractionBlock(torch.nn.Module):
         self.layout = layout
         fin, fe, fout = Irreps(feature_irreps_in), Irreps(irreps_edge_attr), Irreps(feature_irreps_out)
         self.feature_irreps_in, self.irreps_edge_attr, self.feature_irreps_out = fin, fe, fout
-        self.register_buffer("norm_const", torch.tensor(1.0 / math.sqrt(avg_num_neighbors)), persistent=False)
+        # AvgNumNeighborsNorm (nequip/nn/norm.py:7-68): a global value, or one per atom type (a sequence in
+        # type order / the reference's dict after ordering by type_names); norm_const = 1 / sqrt(avg_num_neighbors)
+        ann = [float(avg_num_neighbors)] if isinstance(avg_num_neighbors, (int, float)) else [float(v) for v in avg_num_neighbors]
+        self.register_buffer("norm_const", torch.tensor([1.0 / math.sqrt(v) for v in ann]).reshape(-1, 1), persistent=False)
+        self.norm_shortcut = len(ann) == 1
         self.linear_1 = Linear(fin, fin, layout)
         irreps_mid, instructions = build_tp_instructions(fin, fe, fout)
         self.irreps_mid, self.instructions = irreps_mid, instructions
@@ -391,7 +395,8 @@ class InteractionBlock(torch.nn.Module):
         if tc is not None:
             # inference fast path: every dense block is one grouped 3xTF32 tcgen05 GEMM launch
             x_in = x
-            x = tc["lin1"](x)  # 1/sqrt(avg_num_neighbors) folded into the prepared weights
+            # 1/sqrt(avg_num_neighbors): folded into the prepared weights (global) or a per-atom row scale (per type)
+            x = tc["lin1"](x) if self.norm_shortcut else tc["lin1"](x, self.norm_const.view(-1)[types].view(1, -1).contiguous())
             if halo is not None and not self.is_first_layer:
                 x = halo(x)
             if tc["fused"] is not None and self._use_fused(tc, edge_embedding, x, edge_attrs, edge_index):
@@ -420,7 +425,7 @@ class InteractionBlock(torch.nn.Module):
             return x
         sc = self.sc(x, node_attrs, types, type_table) if self.sc is not None else None
         x = self.linear_1(x)
-        x = x * self.norm_const
+        x = x * (self.norm_const.view(()) if self.norm_shortcut else self.norm_const[types])
         if halo is not None and not self.is_first_layer:
             x = halo(x)
         w = self._edge_weights(edge_embedding)
@@ -445,8 +450,8 @@ class InteractionBlock(torch.nn.Module):
         if any(p.requires_grad for p in self.parameters()) or (type_table is not None and type_table.requires_grad):
             self._note_fallback("parameters require grad (training); freeze them for the inference path")
             return None
-        if self.sc is not None and (types is None or type_table is None):
-            self._note_fallback("self-connection needs atom types + type table")
+        if (self.sc is not None or not self.norm_shortcut) and (types is None or type_table is None):
+            self._note_fallback("self-connection / per-type normalisation need atom types + type table")
             return None
         key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (
             (type_table.data_ptr(), type_table._version) if type_table is not None else ())
@@ -471,7 +476,8 @@ class InteractionBlock(torch.nn.Module):
             fused = dense.FusedRadialTP(lins[0], lins[1], self.tp_scatter._plan, dev)
         blocks = dict(
             fused=fused,
-            lin1=dense.IrrepsLinearGemm(self.linear_1, dev, extra_scale=float(self.norm_const)),
+            lin1=(dense.IrrepsLinearGemm(self.linear_1, dev, extra_scale=float(self.norm_const.view(-1)[0]))
+                  if self.norm_shortcut else dense.IrrepsLinearGemm(self.linear_1, dev, row_scaled=True)),
             lin2=dense.IrrepsLinearGemm(self.linear_2, dev),
             sc=dense.SelfConnectionGemm(self.sc, type_table, dev) if self.sc is not None else None,
             mlp=mlp,
@@ -521,6 +527,15 @@ class NequIPEnergyModel(torch.nn.Module):
         try:
             torch.manual_seed(seed)  # model_builder seeds before construction (model/utils.py:104-230)
             ntypes = len(type_names)
+            if isinstance(avg_num_neighbors, dict):  # per type, keyed by type name (nequip/nn/norm.py:28-31)
+                if set(avg_num_neighbors) != set(type_names):
+                    raise ValueError("avg_num_neighbors: keys must be the type names")
+                avg_num_neighbors = [float(avg_num_neighbors[k]) for k in type_names]
+            elif not isinstance(avg_num_neighbors, (int, float)):
+                avg_num_neighbors = [float(v) for v in avg_num_neighbors]
+                if len(avg_num_neighbors) not in (1, ntypes):
+                    raise ValueError(f"avg_num_neighbors: expected a scalar or {ntypes} values")
+            self.config["avg_num_neighbors"] = avg_num_neighbors
             self.type_embed = torch.nn.Embedding(ntypes, num_features)
             edge_attr = Irreps.spherical_harmonics(l_max)
             prev = Irreps([(num_features, Irrep(0, 1))])

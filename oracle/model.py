@@ -186,7 +186,11 @@ def energy(sd: Dict[str, torch.Tensor], cfg: dict, data: dict, model_dtype=torch
     prev = [(nf, (0, 1))]
     hid = hidden_irreps(l_max, nf, cfg["parity"])
     hiddens = [hid] * (cfg["num_layers"] - 1) + [[(nf, (0, 1))]]
-    norm = 1.0 / math.sqrt(cfg["avg_num_neighbors"])
+    ann = cfg["avg_num_neighbors"]  # global, or one value per type (AvgNumNeighborsNorm, nequip/nn/norm.py:39-68)
+    if isinstance(ann, (int, float)):
+        norm = torch.tensor(1.0 / math.sqrt(ann), dtype=model_dtype)
+    else:
+        norm = torch.tensor([1.0 / math.sqrt(v) for v in ann], dtype=model_dtype)[types].view(-1, 1)
     depth = cfg["radial_mlp_depth"]
     for li, h in enumerate(hiddens):
         scalars = [(m, ir) for m, ir in h if ir[0] == 0 and tp_path_exists(prev, sh_ir, ir)]
@@ -200,7 +204,7 @@ def energy(sd: Dict[str, torch.Tensor], cfg: dict, data: dict, model_dtype=torch
         if li != 0:
             sc = fctp_scalar_attr(x, node_attrs, sd[pre + "sc.weight"].to(model_dtype), prev, nf, conv_out)
         x = linear(x, sd[pre + "linear_1.weight"].to(model_dtype), prev, prev)
-        x = x * torch.tensor(norm, dtype=model_dtype)
+        x = x * norm
         dims = [cfg["num_bessels"]] + depth * [cfg["radial_mlp_width"]] + [otp.weight_numel(prev, sh_ir, ins)]
         ws, alphas = [], []
         for q in range(depth + 1):

@@ -267,3 +267,31 @@ def test_model_construction_loads_no_native_code_and_strict_flag_propagates():
             "print('ok')\n") % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_reference_checkpoint_key_mapping_round_trip():
+    """nequip_b200/nn/checkpoint.py: parameters travel under the reference's module names
+    (nequip/model/nequip_models.py:288-399) with any wrapper prefix; e3nn buffers are ignored."""
+    from nequip_b200.nn.checkpoint import load_reference_state_dict, reference_key_map, to_reference_state_dict
+    from nequip_b200.nn.model import NequIPEnergyModel
+
+    kw = dict(r_max=4.0, type_names=["H", "O"], l_max=2, num_layers=3, num_features=8, radial_mlp_width=16)
+    a = NequIPEnergyModel(per_type_energy_scales=[1.5, 2.0], per_type_energy_shifts=0.25, seed=1, **kw)
+    ref = to_reference_state_dict(a, prefix="model.func.")
+    assert "model.func.type_embed.embed_module.weight" in ref
+    assert "model.func.layer2_convnet.conv.sc.weight" in ref and "model.func.layer0_convnet.conv.sc.weight" not in ref
+    assert "model.func.per_atom_energy_readout.mlp_module.mlp.0.weight" in ref
+    assert len(ref) == len(reference_key_map(3))
+    # what a real checkpoint additionally holds: e3nn buffers of the un-used self.tp, output masks
+    ref["model.func.layer1_convnet.conv.tp_scatter.tp._w3j_1_1_2"] = torch.zeros(3)
+    ref["model.func.layer1_convnet.conv.linear_1.output_mask"] = torch.ones(5)
+    b = NequIPEnergyModel(per_type_energy_scales=[1.0, 1.0], per_type_energy_shifts=[0.0, 0.0], seed=2, **kw)
+    missing, unexpected = load_reference_state_dict(b, ref)
+    assert missing == [] and unexpected == []
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    ref["model.func.something_else.weight"] = torch.zeros(2)
+    with pytest.raises(KeyError):
+        load_reference_state_dict(b, ref)
+    with pytest.raises(ValueError):
+        load_reference_state_dict(b, {"func.type_embed.embed_module.weight": torch.zeros(3, 3)}, strict=False)

@@ -191,3 +191,82 @@ def test_edge_force_branch_matches_oracle():
     e_pos = model(D.to_device(sysd, "cuda"), compute_forces=False)["total_energy"]
     assert abs(float(out["total_energy"]) - float(e_pos)) <= 1e-6 * float(out["atomic_energy"].abs().sum())
     assert abs(float(out["total_energy"]) - float(e_ref)) <= 1e-5 * float(out["atomic_energy"].abs().sum())
+
+
+@pytest.mark.timeout(900)
+def test_bench_size_fp32_kernels_vs_fp64_kernels():
+    """The frame bench.py times (10 648 atoms, 588 616 edges, l_max 2, 64 features): the float32 product path
+    (tcgen05 3xTF32 GEMMs, FFMA2 TP kernels, graph-free eager call) against the float64 kernels of the same model
+    and weights -- no oracle can run at this size in seconds, the fp64 path (itself oracle-checked at 125-1000 atoms)
+    is the yardstick.  1e-5 relative on forces, energy and per-atom energies."""
+    sysd = D.make_system("li3po4", 22, r_max=5.0, seed=0)
+    meta = sysd.pop("_meta")
+    mk = dict(l_max=2, num_layers=4, num_features=64, radial_mlp_depth=1, radial_mlp_width=128)
+    m32 = NequIPEnergyModel(r_max=5.0, type_names=meta["type_names"], parity=True,
+                            avg_num_neighbors=meta["avg_num_neighbors"], strict_fast_path=True, **mk).cuda()
+    for p in m32.parameters():
+        p.requires_grad_(False)
+    m64 = NequIPEnergyModel(r_max=5.0, type_names=meta["type_names"], parity=True,
+                            avg_num_neighbors=meta["avg_num_neighbors"], model_dtype=torch.float64, **mk).cuda()
+    m64.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in m32.state_dict().items()})
+    for p in m64.parameters():
+        p.requires_grad_(False)
+    dev = D.to_device(sysd, "cuda")
+    out32 = m32(dev)
+    f32, e32, ea32 = out32["forces"].clone(), out32["total_energy"].clone(), out32["atomic_energy"].clone()
+    del out32
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out64 = m64(dev)
+    fscale = float(out64["forces"].abs().max())
+    ferr = float((f32 - out64["forces"]).abs().max()) / fscale
+    eerr = abs(float(e32) - float(out64["total_energy"])) / float(out64["atomic_energy"].abs().sum())
+    aerr = float((ea32 - out64["atomic_energy"]).abs().max()) / float(out64["atomic_energy"].abs().max())
+    print(f"bench-size fp32 vs fp64: max|dF|/max|F| = {ferr:.2e}, |dE|/sum|E_i| = {eerr:.2e}, max|dE_i|/max|E_i| = {aerr:.2e}")
+    assert ferr <= 1e-5 and eerr <= 1e-5 and aerr <= 1e-5
+
+
+@pytest.mark.timeout(900)
+def test_bench_model_on_1000_atoms_matches_oracle():
+    """The bench model family (l_max 2, 4 layers, 64 features, radial 1x128, frozen weights -> tensor-core dense
+    blocks) on a 1000-atom Li3PO4-like box against the oracle with identical weights."""
+    sysd = D.make_system("li3po4", 10, r_max=5.0, seed=4)
+    meta = sysd.pop("_meta")
+    mk = dict(l_max=2, num_layers=4, num_features=64, radial_mlp_depth=1, radial_mlp_width=128)
+    model = NequIPEnergyModel(r_max=5.0, type_names=meta["type_names"], parity=True,
+                              avg_num_neighbors=meta["avg_num_neighbors"], strict_fast_path=True, **mk).cuda()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    out = model(D.to_device(sysd, "cuda"))
+    e_ref, ea_ref, f_ref = omodel.energy_and_forces(model.state_dict(), model.config, sysd, torch.float32, tp_chunk=20000)
+    ferr = float((out["forces"].cpu() - f_ref).abs().max()) / float(f_ref.abs().max())
+    eerr = abs(float(out["total_energy"]) - float(e_ref)) / float(ea_ref.abs().sum())
+    print(f"1000 atoms vs oracle: max|dF|/max|F| = {ferr:.2e}, |dE|/sum|E_i| = {eerr:.2e}")
+    assert ferr <= 1e-5 and eerr <= 1e-5
+
+
+@pytest.mark.parametrize("frozen", [True, False])
+def test_per_type_avg_num_neighbors_matches_oracle(frozen):
+    """AvgNumNeighborsNorm with one value per atom type (nequip/nn/norm.py:28-68): a per-atom row scale of the
+    linear_1 GEMM on the tensor-core path, an elementwise factor on the torch path."""
+    sysd = D.make_system("li3po4", 6, r_max=5.0, seed=7)
+    meta = sysd.pop("_meta")
+    ann = {"Li": 31.0, "P": 58.5, "O": 47.25}
+    model = NequIPEnergyModel(r_max=5.0, type_names=meta["type_names"], parity=True, avg_num_neighbors=ann,
+                              l_max=2, num_layers=3, num_features=32, strict_fast_path=frozen).cuda()
+    if frozen:
+        for p in model.parameters():
+            p.requires_grad_(False)
+    out = model(D.to_device(sysd, "cuda"))
+    assert model.config["avg_num_neighbors"] == [31.0, 58.5, 47.25]
+    e_ref, ea_ref, f_ref = omodel.energy_and_forces(model.state_dict(), model.config, sysd, torch.float32)
+    assert abs(float(out["total_energy"]) - float(e_ref)) <= 1e-5 * float(ea_ref.abs().sum())
+    assert float((out["forces"].cpu() - f_ref).abs().max()) <= 1e-5 * float(f_ref.abs().max())
+    # and it differs from the global normalisation (the test would be vacuous otherwise)
+    m2 = NequIPEnergyModel(r_max=5.0, type_names=meta["type_names"], parity=True, avg_num_neighbors=45.0,
+                           l_max=2, num_layers=3, num_features=32).cuda()
+    m2.load_state_dict(model.state_dict())
+    e2 = m2(D.to_device(sysd, "cuda"), compute_forces=False)["total_energy"]
+    assert abs(float(e2) - float(out["total_energy"])) > 1e-4 * float(ea_ref.abs().sum())
