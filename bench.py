@@ -50,7 +50,8 @@ WORKLOADS = {
 # the whole CPU run stays within CPU_BUDGET_S -- at least 1000 atoms whenever that fits.
 CPU_SAMPLE_NSIDE_MAX = {"li3po4_10k_l2_f64": 10, "water_1k_l2_f32": 10, "asi_50k_l3_f32": 11, "tiny": 4}
 CPU_SAMPLE_NSIDE_MIN = {"li3po4_10k_l2_f64": 6, "water_1k_l2_f32": 6, "asi_50k_l3_f32": 7, "tiny": 4}
-CPU_BUDGET_S = 200.0
+CPU_BUDGET_S = 200.0      # cpu_baseline leg of the own arm (3 steps)
+REF_ARM_BUDGET_S = 300.0  # --impl reference: all of its --steps + --warmup steps ("a few minutes")
 R_MAX = 5.0
 
 
@@ -153,12 +154,13 @@ def pick_threads(workload):
     return best, times, times[best] / sysd["pos"].shape[0]
 
 
-def pick_sample_nside(workload, sec_per_atom, nsteps):
-    """Largest box (n_side^3 atoms) whose ``nsteps`` CPU steps fit CPU_BUDGET_S at the measured per-atom cost."""
+def pick_sample_nside(workload, sec_per_atom, nsteps, budget_s=None):
+    """Largest box (n_side^3 atoms) whose ``nsteps`` CPU steps fit the budget at the measured per-atom cost."""
+    budget_s = CPU_BUDGET_S if budget_s is None else budget_s
     lo, hi = CPU_SAMPLE_NSIDE_MIN[workload], CPU_SAMPLE_NSIDE_MAX[workload]
     ns = lo
     for n in range(lo, hi + 1):
-        if nsteps * sec_per_atom * n ** 3 <= CPU_BUDGET_S:
+        if nsteps * sec_per_atom * n ** 3 <= budget_s:
             ns = n
     return ns
 
@@ -172,7 +174,7 @@ def run_reference(args, rank, world):
     from oracle import model as omodel
 
     cores, _, spa = pick_threads(args.workload)
-    ns = pick_sample_nside(args.workload, spa, args.steps + args.warmup)
+    ns = pick_sample_nside(args.workload, spa, args.steps + args.warmup, budget_s=REF_ARM_BUDGET_S)
     sysd, meta, mk = build_system(args.workload, seed=0, n_side=ns)
     model = NequIPEnergyModel(r_max=R_MAX, type_names=meta["type_names"], parity=True,
                               avg_num_neighbors=meta["avg_num_neighbors"], **mk)
@@ -192,7 +194,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "atom-steps/sec (energy+forces)", "value": val, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "CPU e3nn-formulation path (oracle port), bounded sample"},
+        # the own arm's workload and model keys; what was actually evaluated per step is `cpu_baseline.sample`
+        "config": {"workload": args.workload, "r_max": R_MAX, "parity": True, **mk,
+                   "atoms_per_step_sample": n_atoms, "edges_per_step_sample": int(sysd["edge_index"].shape[1]),
+                   "note": ("CPU e3nn-formulation path (oracle port) on a bounded sample of the workload: a smaller box of "
+                            "the same structure kind, density, r_max and model (atom-steps/s is per atom)")},
         "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -466,14 +472,25 @@ def main():
     for layer in model.layers:
         layer.conv.strict_fast_path = True  # a torch.matmul fallback of a dense block must not be timed silently
 
-    graphed = None
+    graphed, graph_error = None, None
     if not args.no_graph:
         from nequip_b200.graph import GraphedEnergyForces, GraphedShardedEnergyForces
 
-        if halo_mode:  # the sharded step incl. its NCCL exchanges as one graph per rank
-            graphed = GraphedShardedEnergyForces(model, resident, plan, halo)
-        else:
-            graphed = GraphedEnergyForces(model, resident)  # captured once; replayed every step
+        try:
+            if halo_mode:  # the sharded step incl. its NCCL exchanges as one graph per rank
+                graphed = GraphedShardedEnergyForces(model, resident, plan, halo)
+            else:
+                graphed = GraphedEnergyForces(model, resident)  # captured once; replayed every step
+        except Exception as exc:  # e.g. a driver / NCCL build that cannot capture: time the eager step, and say so
+            graphed, graph_error = None, f"{type(exc).__name__}: {exc}"[:300]
+            print(f"[bench rank {rank}] CUDA-graph capture failed, falling back to eager launches: {graph_error}",
+                  file=sys.stderr, flush=True)
+        if world > 1:  # either every rank replays a graph or none does (the collectives must match)
+            ok = torch.tensor([1 if graphed is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                graphed = None
+                graph_error = graph_error or "capture failed on another rank"
 
     def step_resident():
         if graphed is not None:
@@ -618,7 +635,7 @@ def main():
                                 if halo_mode
                                 else f"dp{world} over frames (one {n_atoms}-atom frame per GPU)"),
                 "launch": ("one CUDA-graph replay per step (nequip_b200/graph.py)" if graphed is not None
-                           else "eager launches"),
+                           else ("eager launches" + (f" (graph capture failed: {graph_error})" if graph_error else ""))),
                 "radial_tp_path": [
                     {"layer": i, "choice": ("fused (nqb_tp_fused_fwd)" if l.conv._fused_choice else "k_gemm3x + tp_fwd*"),
                      **{k: round(v, 4) for k, v in (getattr(l.conv, "fused_timing_ms", None) or {}).items()}}

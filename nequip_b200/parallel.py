@@ -7,16 +7,20 @@ model as owned + ghost atoms and a per-layer ghost-feature exchange hook
 ``nequip/integrations/lammps_mliap/lmp_mliap_wrapper.py:202-219``).  This module is the
 B200-native equivalent with ``torch.distributed`` (NCCL over NVLink; gloo in the CPU tests):
 
-* atoms are split into contiguous slabs along x; a rank *owns* its slab and additionally
-  holds *ghost* copies of every non-owned atom that is the source of an edge whose
-  destination it owns -- so every scatter destination is local and the TP+scatter kernel
-  never crosses ranks;
+* atoms are split into ``gx x gy x gz`` bricks of equal atom counts (``brick_grid`` picks the
+  factorisation with the smallest halo volume: slabs for an elongated box, 3-D bricks for a cubic
+  one); a rank *owns* its brick and additionally holds *ghost* copies of every non-owned atom that
+  is the source of an edge whose destination it owns -- so every scatter destination is local and
+  the TP+scatter kernel never crosses ranks;
 * before every interaction layer >= 1 the owners' current features are sent to the ranks
-  that hold ghosts of them (``all_to_all_single`` with split sizes); the backward of that
-  exchange is the transposed exchange with accumulation into the owner rows (what LAMMPS'
-  ``reverse_exchange`` does);
-* energies: sum over owned atoms then one all-reduce; forces: each rank's d E_local / d pos
-  over its owned + ghost atoms is scattered into a global ``[N, 3]`` buffer and all-reduced.
+  that hold ghosts of them (``all_to_all_single`` with split sizes, received straight into the
+  tail of the feature buffer); the backward of that exchange is the transposed exchange with
+  accumulation into the owner rows (what LAMMPS' ``reverse_exchange`` does);
+* energies: sum over owned atoms then one 8-byte all-reduce; forces stay with their owners: the
+  gradient w.r.t. ghost positions travels back through one more transposed exchange
+  (``owner_reduce``, O(N / P) per rank).  A dense ``[N, 3]`` all-reduce (``reduce_forces="global"``)
+  is kept for tests and small frames.
+* the whole sharded step is capturable as one CUDA graph per rank (``graph.GraphedShardedEnergyForces``).
 """
 from __future__ import annotations
 
