@@ -315,6 +315,12 @@ def kernel_rooflines(model, resident, n_atoms, n_edges, reps, ms_step, dev):
             w = torch.empty(E, W, device=dev)
             gh = torch.empty(E, K, device=dev)
             flops3 = 3 * 2.0 * E * K * W
+            if emb.shape[1] == 8 and K == 128:  # the CUDA-core hidden layer (k_hidden_fwd / k_hidden_bwd), both directions
+                gemb = torch.empty_like(emb)
+                ms = _time_cuda(lambda: ops.mlp_hidden_fwd(emb, mlp.w1s, h, None), reps)
+                add("k_hidden_fwd", hbm_entry("k_hidden_fwd (radial MLP first layer + SiLU, CUDA cores)", ms, 4 * E * (8 + K), li))
+                ms = _time_cuda(lambda: ops.mlp_hidden_bwd(emb, mlp.w1s, h, gemb), reps)
+                add("k_hidden_bwd", hbm_entry("k_hidden_bwd (its backward, pre-activation recomputed)", ms, 4 * E * (8 + K + 8), li))
             tc = conv._tc_cache[1] if conv._tc_cache else None
             fused = tc["fused"] if (tc and tc["fused"] is not None and (conv.use_fused_radial_tp is True or conv._fused_choice)) else None
             if fused is not None:
@@ -640,6 +646,7 @@ def main():
                     {"layer": i, "choice": ("fused (nqb_tp_fused_fwd)" if l.conv._fused_choice else "k_gemm3x + tp_fwd*"),
                      **{k: round(v, 4) for k, v in (getattr(l.conv, "fused_timing_ms", None) or {}).items()}}
                     for i, l in enumerate(model.layers)],
+                "hidden_layer_kernels": "v%d (nqb_mlp.cu)" % ops.mlp_hidden_variant(0),
                 "l2_policy": "inputs larger than L2 (edge weights of one layer: %.2f GB)" % (
                     n_edges * max(l.conv.tp_scatter.weight_numel for l in model.layers) * 4 / 1e9),
             },

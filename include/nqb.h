@@ -177,6 +177,11 @@ int nqb_mlp_hidden_fwd(const float* emb, const float* W1s, int64_t E, int num_be
                        float* h_lo, nqb_stream_t st);
 int nqb_mlp_hidden_bwd(const float* emb, const float* W1s, const float* grad_h, int64_t E, int num_bessel,
                        int hidden, float* grad_emb, nqb_stream_t st);
+/* Kernel generation of the two calls above: 2 = batched kernels (32 edges per warp, prefetched basis values, packed
+ * FFMA2, one 128-byte grad_emb row per four edges), 1 = the round-1 kernels (one edge per warp iteration).  Returns the
+ * previous value; 0 only queries.  Default: the library's build-time choice, overridden by the environment variable
+ * NQB_HIDDEN_VARIANT=1|2.  Not thread safe -- call between launches (A/B timing, parity tests). */
+int nqb_mlp_hidden_set_variant(int variant);
 
 /* Grouped fp32-accurate GEMM on the tensor cores (tcgen05 kind::tf32, 3xTF32, segmented fp32
  * accumulation):  C_p[M, N_p] (+)= rowscale_p[m] * A_p[M, K_p] @ B_p[K_p, N_p]  for a list of problems

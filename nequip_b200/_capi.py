@@ -58,6 +58,7 @@ SIGNATURES = {
         _i32, [_i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nqb_mlp_hidden_fwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "nqb_mlp_hidden_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "nqb_mlp_hidden_set_variant": (_i32, [_i32]),
     "nqb_gemm_prepared_floats": (_i64, [_i32, _i32]),
     "nqb_gemm_prepare": (_i32, [_vp, _i64, _i32, _i32, _i32, C.c_float, _vp, _vp]),
     "nqb_gemm_t_prepared_floats": (_i64, [_i32, _i32]),

@@ -647,6 +647,12 @@ def mlp_hidden_fwd(emb: torch.Tensor, w1s: torch.Tensor, h: torch.Tensor, h_lo: 
                                                _ptr(h_lo), _stream()), "nqb_mlp_hidden_fwd")
 
 
+def mlp_hidden_variant(variant: int = 0) -> int:
+    """Kernel generation of ``mlp_hidden_fwd/bwd``: 2 = batched kernels, 1 = round-1 kernels; 0 only queries.
+    Returns the previous value (``nqb_mlp_hidden_set_variant``; A/B timing and the variant parity test)."""
+    return int(_capi.lib().nqb_mlp_hidden_set_variant(int(variant)))
+
+
 def mlp_hidden_bwd(emb: torch.Tensor, w1s: torch.Tensor, gh: torch.Tensor, gemb: torch.Tensor) -> None:
     """``gemb = (gh * silu'(emb @ w1s)) @ w1s^T``."""
     _require_cuda(emb, w1s, gh, gemb)
