@@ -295,3 +295,43 @@ def test_reference_checkpoint_key_mapping_round_trip():
         load_reference_state_dict(b, ref)
     with pytest.raises(ValueError):
         load_reference_state_dict(b, {"func.type_embed.embed_module.weight": torch.zeros(3, 3)}, strict=False)
+
+
+def test_bench_reference_arm_json_contract():
+    """``bench.py --impl reference`` (the CPU arm the driver times beside the GPU arm): one JSON line with the metric /
+    unit / higher_is_better of the own arm, ``impl``, a ``cpu_baseline`` describing the run, zero-copy ``e2e`` and the
+    workload + model keys in ``config``."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "atom-steps/sec (energy+forces)"
+    assert line["unit"] == "atom-steps/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    cfg = line["config"]
+    assert cfg["workload"] == "tiny" and cfg["l_max"] == 2 and cfg["num_layers"] == 3 and cfg["num_features"] == 8
+    assert cfg["atoms_per_step_sample"] > 0 and cfg["edges_per_step_sample"] > 0
+
+
+def test_bench_cpu_sample_size_respects_the_budget():
+    sys_path_bench = os.path.join(ROOT, "bench.py")
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("nqb_bench", sys_path_bench)
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = "li3po4_10k_l2_f64"
+    lo, hi = bench.CPU_SAMPLE_NSIDE_MIN[wl], bench.CPU_SAMPLE_NSIDE_MAX[wl]
+    assert bench.pick_sample_nside(wl, 1e-9, 3) == hi           # cheap: the largest sample (1000 atoms)
+    assert bench.pick_sample_nside(wl, 1e3, 3) == lo            # hopeless: the smallest allowed
+    n = bench.pick_sample_nside(wl, 0.0137, 25, budget_s=bench.REF_ARM_BUDGET_S)  # the driver's 20 + 5 steps on this pool's host
+    assert lo <= n <= hi and 25 * 0.0137 * n ** 3 <= bench.REF_ARM_BUDGET_S < 25 * 0.0137 * (n + 1) ** 3
+    # algorithmic bytes of the TP kernels (SURVEY 8d): forward = x + Y + w + out + two index arrays
+    sig = type("S", (), dict(d_in=10, s_dim=4, weight_numel=6, d_out=20))
+    assert bench.tp_algorithmic_bytes(sig, 3, 7) == 4 * (3 * 10 + 7 * 4 + 7 * 6 + 3 * 20) + 16 * 7
