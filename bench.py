@@ -243,6 +243,18 @@ def ncu_summary(kernel, field):
     return None
 
 
+def force_sum_vector(forces):
+    """[sum Fx, sum Fy, sum Fz, sum |F|, 1] (float64) of one rank's forces -- summed over the ranks this is the
+    size-independent parity property of the step: the forces of a periodic frame add up to zero (Newton's third law),
+    and under the halo partition they only do if every ghost contribution reached its owner."""
+    f = forces.detach().double().reshape(-1, 3)
+    v = torch.zeros(5, dtype=torch.float64, device=f.device)
+    v[:3] = f.sum(0)
+    v[3] = f.abs().sum()
+    v[4] = 1.0
+    return v
+
+
 def _time_cuda(fn, reps):
     for _ in range(3):
         fn()
@@ -604,6 +616,20 @@ def main():
     if graphed is not None:
         graphed.check_sorted()  # the in-graph "edges grouped by destination" flag of the last replay
 
+    # size-independent property of the timed step, on this hardware and at this size: sum of all forces = 0
+    chk = torch.zeros(5, dtype=torch.float64, device=dev)
+    try:
+        chk = force_sum_vector(step_resident()["forces"])
+    except Exception as exc:  # reported, never fatal (the collective below must still be entered by every rank)
+        print(f"[bench rank {rank}] force-sum check failed: {type(exc).__name__}: {exc}", file=sys.stderr, flush=True)
+        chk = torch.zeros(5, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(chk)
+    chk = chk.tolist()
+    checks = {"sum_forces_over_sum_abs_forces": (math.sqrt(chk[0] ** 2 + chk[1] ** 2 + chk[2] ** 2) / chk[3]) if chk[3] > 0 else None,
+              "ranks_reporting": int(round(chk[4])),
+              "note": "Newton's third law over the whole frame (all ranks): a lost or doubled ghost contribution shows as ~1e-2"}
+
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     d2h = f_host.numel() * 8 + 8
 
@@ -657,6 +683,7 @@ def main():
                 "h2d_bytes_per_step": int(host["pos"].numel() * 8), "d2h_bytes_per_step": d2h,
                 "note": "positions in, forces out; neighbour list (cell list) built on the GPU inside the timed region"}),
             "gpu_launches": launches,
+            "checks": checks,
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,

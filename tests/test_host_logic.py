@@ -335,3 +335,19 @@ def test_bench_cpu_sample_size_respects_the_budget():
     # algorithmic bytes of the TP kernels: forward = x + Y + w + out + two index arrays
     sig = type("S", (), dict(d_in=10, s_dim=4, weight_numel=6, d_out=20))
     assert bench.tp_algorithmic_bytes(sig, 3, 7) == 4 * (3 * 10 + 7 * 4 + 7 * 6 + 3 * 20) + 16 * 7
+
+
+def test_bench_force_sum_property_vector():
+    """bench.py's size-independent parity property (sum of all forces = 0): the per-rank vector that is all-reduced."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("nqb_bench2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    f = torch.randn(50, 3, dtype=torch.float32)
+    v = bench.force_sum_vector(f)
+    assert v.dtype == torch.float64 and v.shape == (5,)
+    assert torch.allclose(v[:3], f.double().sum(0)) and float(v[3]) == pytest.approx(float(f.double().abs().sum())) and float(v[4]) == 1.0
+    # two "ranks" whose forces cancel
+    tot = bench.force_sum_vector(f) + bench.force_sum_vector(-f)
+    assert float(tot[:3].abs().max()) == 0.0 and float(tot[4]) == 2.0
