@@ -20,7 +20,9 @@ r_max 5 A -- on a synthetic ~10k-atom Li3PO4-like periodic box (10 648 atoms, ~5
 N > 1 (default): ONE frame partitioned by atoms into N bricks with halo (ghost) atoms -- the north_star
 partition: per-layer NCCL halo exchange of ghost features, energy all-reduce, ghost-force reduction to the
 owners; the whole sharded step is one CUDA-graph replay per rank.  `--scaling weak` (default) grows the frame
-with N (N x 10 648 atoms, box elongated along x), `--scaling strong` splits the 10 648-atom frame.
+with N (the N-fold periodic supercell of the N = 1 frame along x: N x 10 648 atoms), `--scaling strong` splits the
+10 648-atom frame.  `checks`: sum of all forces = 0, and in halo mode `partition_parity` = forces / energy of the
+sharded frame against the UNSHARDED base frame evaluated on each rank (every atom is a periodic copy of a base atom).
 `--decomp frames` keeps the round-1 mode (one independent frame per GPU, the reference's DDP axis).
 """
 import argparse
@@ -127,6 +129,21 @@ def build_system(workload, seed, n_side=None):
     sysd = D.make_system(kind, n_side or ns, r_max=R_MAX, seed=seed)
     meta = sysd.pop("_meta")
     return sysd, meta, mk
+
+
+def build_partitioned_frame(workload, world, scaling):
+    """The ONE frame that ``world`` ranks share in halo mode, built from the N = 1 workload frame (seed 0):
+    ``weak``  : its ``world``-fold periodic supercell along x (world x the atoms, box elongated along x);
+    ``strong``: the frame itself.
+    Either way every atom of the partitioned frame is a periodic copy of a base-frame atom, so the energies and forces
+    of the sharded computation must equal those of the UNSHARDED base frame (tiled) -- checked on the hardware after
+    the timed region (``checks.partition_parity``).  Returns (full frame, base frame, meta, model kwargs, copies)."""
+    from nequip_b200 import data as D
+
+    base, meta, mk = build_system(workload, seed=0)
+    copies = world if scaling == "weak" else 1
+    full = D.replicate_frame(base, copies, r_max=R_MAX, axis=0) if copies > 1 else dict(base)
+    return full, base, meta, mk, copies
 
 
 def pick_threads(workload):
@@ -253,6 +270,65 @@ def force_sum_vector(forces):
     v[3] = f.abs().sum()
     v[4] = 1.0
     return v
+
+
+def parity_checks(step, unsharded_model, base_frame, copies, owned_ids, halo_mode, world, rank, dev):
+    """Parity properties of the step that was timed, evaluated on the hardware and at the size of the run.
+
+    ``step()`` is the timed step (in halo mode it contains collectives: it is called unconditionally by every rank);
+    everything inside the try blocks is rank-local, so a failure there is reported on stderr but can never
+    desynchronise the ranks, and every collective below is entered by every rank.
+    (1) Newton's third law: the forces of all atoms, over all ranks, add up to zero.
+    (2) halo mode: the partitioned frame is the ``copies``-fold periodic supercell of ``base_frame`` (or the base frame
+        itself), so owned atom g must carry the force of base atom ``g % n_base`` in the UNSHARDED call
+        ``unsharded_model(base_frame)`` (eager, same weights and kernels, evaluated on each rank), and the total energy
+        must be ``copies`` times the base frame's."""
+    import torch.distributed as dist
+
+    last = step()
+    f_last = last["forces"].detach().clone()
+    e_last = last["total_energy"].detach().double().reshape(-1)[:1].clone()
+    chk = torch.zeros(5, dtype=torch.float64, device=dev)
+    try:
+        chk = force_sum_vector(f_last).to(dev)
+    except Exception as exc:
+        print(f"[bench rank {rank}] force-sum check failed: {type(exc).__name__}: {exc}", file=sys.stderr, flush=True)
+        chk = torch.zeros(5, dtype=torch.float64, device=dev)
+    par = torch.zeros(4, dtype=torch.float64, device=dev)  # max|dF|, max|F_base|, |dE| / (copies sum|E_i|), rank ok
+    n_base = 0
+    if halo_mode:
+        try:
+            n_base = int(base_frame["pos"].shape[0])
+            ref = unsharded_model(base_frame)
+            idx = (owned_ids % n_base).to(f_last.device)
+            par[0] = (f_last - ref["forces"][idx]).abs().max()
+            par[1] = ref["forces"].abs().max()
+            par[2] = (e_last - copies * ref["total_energy"].detach().double().reshape(-1)[:1]).abs().max() / (
+                copies * ref["atomic_energy"].detach().double().abs().sum())
+            par[3] = 1.0
+            del ref
+        except Exception as exc:
+            print(f"[bench rank {rank}] partition-parity check failed: {type(exc).__name__}: {exc}", file=sys.stderr, flush=True)
+            par = torch.zeros(4, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(chk)
+        ok_ranks = par[3:4].clone()
+        dist.all_reduce(par, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ok_ranks)
+        par[3] = ok_ranks[0]
+    chk, par = chk.tolist(), par.tolist()
+    checks = {"sum_forces_over_sum_abs_forces": (math.sqrt(chk[0] ** 2 + chk[1] ** 2 + chk[2] ** 2) / chk[3]) if chk[3] > 0 else None,
+              "ranks_reporting": int(round(chk[4])),
+              "note": "Newton's third law over the whole frame (all ranks): a lost or doubled ghost contribution shows as ~1e-2"}
+    if halo_mode:
+        checks["partition_parity"] = {
+            "max_dF_over_max_F": (par[0] / par[1]) if par[1] > 0 else None,
+            "dE_over_sum_abs_Ei": par[2] if par[3] > 0 else None,
+            "ranks_reporting": int(round(par[3])),
+            "what": (f"forces of every owned atom and the total energy of the frame sharded over {world} ranks vs the "
+                     f"UNSHARDED {n_base}-atom base frame evaluated eagerly on each rank (the sharded frame is its "
+                     f"{copies}-fold periodic supercell); max over ranks, fp32 kernels: expect <= 1e-5")}
+    return checks
 
 
 def _time_cuda(fn, reps):
@@ -446,31 +522,17 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
 
     halo_mode = world > 1 and args.decomp == "halo"
+    base_frame, copies = None, 1
     if halo_mode:
         from nequip_b200 import parallel as P
-        import numpy as np
 
-        kind, ns, mk = WORKLOADS[args.workload]
-        pr = D.PRESETS[kind]
-        a = (1.0 / pr["density"]) ** (1.0 / 3.0)
-        nx = ns * world if args.scaling == "weak" else ns  # weak: ONE frame of world x (ns^3) atoms, elongated along x
-        rng = np.random.default_rng(0)
-        gx, gy = np.arange(nx, dtype=np.float64), np.arange(ns, dtype=np.float64)
-        zz, yy, xx = np.meshgrid(gy, gy, gx, indexing="ij")
-        pos_np = (np.stack([xx.ravel(), yy.ravel(), zz.ravel()], 1) + 0.5 + rng.uniform(-0.22, 0.22, (xx.size, 3))) * a
-        cell_np = np.diag([nx * a, ns * a, ns * a])
-        ratios = np.asarray(pr["ratios"], dtype=np.float64)
-        types_np = np.random.default_rng(1).choice(len(ratios), size=pos_np.shape[0], p=ratios / ratios.sum())
-        ei_np, sh_np = D.neighbor_list(pos_np, cell_np, R_MAX)
-        full = {"pos": torch.from_numpy(pos_np), "cell": torch.from_numpy(cell_np),
-                "atom_types": torch.from_numpy(types_np.astype(np.int64)), "edge_index": torch.from_numpy(ei_np),
-                "edge_cell_shift": torch.from_numpy(sh_np)}
-        meta = dict(type_names=list(pr["type_names"]), avg_num_neighbors=float(ei_np.shape[1]) / pos_np.shape[0])
-        grid = P.brick_grid(world, [nx * a, ns * a, ns * a], halo=R_MAX)
+        full, base_frame, meta, mk, copies = build_partitioned_frame(args.workload, world, args.scaling)
+        lengths = torch.diagonal(full["cell"]).tolist()
+        grid = P.brick_grid(world, lengths, halo=R_MAX)
         owner = P.brick_owner(full["pos"], grid)
         plan = P.make_plans(full["edge_index"], owner, world)[rank]
         sysd = P.shard_data(full, plan)
-        n_total_atoms = pos_np.shape[0]
+        n_total_atoms = full["pos"].shape[0]
         del full
     else:
         # every rank owns its own frame (same size/density, different seed)
@@ -616,19 +678,9 @@ def main():
     if graphed is not None:
         graphed.check_sorted()  # the in-graph "edges grouped by destination" flag of the last replay
 
-    # size-independent property of the timed step, on this hardware and at this size: sum of all forces = 0
-    chk = torch.zeros(5, dtype=torch.float64, device=dev)
-    try:
-        chk = force_sum_vector(step_resident()["forces"])
-    except Exception as exc:  # reported, never fatal (the collective below must still be entered by every rank)
-        print(f"[bench rank {rank}] force-sum check failed: {type(exc).__name__}: {exc}", file=sys.stderr, flush=True)
-        chk = torch.zeros(5, dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(chk)
-    chk = chk.tolist()
-    checks = {"sum_forces_over_sum_abs_forces": (math.sqrt(chk[0] ** 2 + chk[1] ** 2 + chk[2] ** 2) / chk[3]) if chk[3] > 0 else None,
-              "ranks_reporting": int(round(chk[4])),
-              "note": "Newton's third law over the whole frame (all ranks): a lost or doubled ghost contribution shows as ~1e-2"}
+    # ---- parity properties of the very step that was timed, on this hardware and at this size
+    checks = parity_checks(step_resident, (lambda frame: model(D.to_device(frame, dev))), base_frame, copies,
+                           (plan.owned if halo_mode else None), halo_mode, world, rank, dev)
 
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     d2h = f_host.numel() * 8 + 8
@@ -661,7 +713,8 @@ def main():
             "config": {
                 "workload": args.workload,
                 "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges, "r_max": R_MAX, "parity": True, **mk,
-                "parallelism": (f"halo{world}: one {total_atoms}-atom frame partitioned by atoms into {grid[0]}x{grid[1]}x{grid[2]} "
+                "parallelism": (f"halo{world}: one {total_atoms}-atom frame (the {copies}-fold periodic supercell of the N=1 "
+                                f"workload frame) partitioned by atoms into {grid[0]}x{grid[1]}x{grid[2]} "
                                 f"bricks, {plan.n_own} owned + {plan.n_ghost} ghost atoms on rank 0, per-layer NCCL halo "
                                 f"exchange of ghost features, energy all-reduce, ghost forces reduced to owners ({args.scaling} scaling)"
                                 if halo_mode

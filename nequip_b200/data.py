@@ -142,5 +142,30 @@ def make_system(kind: str, n_side: int, r_max: float = 5.0, seed: int = 0) -> Di
     }
 
 
+def replicate_frame(data: Dict[str, torch.Tensor], copies: int, r_max: float = 5.0, axis: int = 0) -> Dict[str, torch.Tensor]:
+    """``copies``-fold periodic supercell of an orthorhombic frame along ``axis``: atom ``c * n + b`` is base atom ``b``
+    shifted by ``c`` cell lengths, the cell grows ``copies`` times along ``axis``, the neighbour list is rebuilt.
+    By periodicity every copy of an atom has the energy and force of the base atom -- the property bench.py uses to
+    check a frame sharded over N GPUs against the unsharded base frame (weak scaling = the N-fold supercell)."""
+    pos = data["pos"].double().numpy()
+    cell = data["cell"].double().numpy().reshape(3, 3)
+    if copies < 1 or np.abs(cell - np.diag(np.diagonal(cell))).max() > 0:
+        raise ValueError("replicate_frame: needs copies >= 1 and an orthorhombic (diagonal) cell")
+    n = pos.shape[0]
+    step = np.zeros(3)
+    step[axis] = cell[axis, axis]
+    big = np.concatenate([pos + c * step for c in range(copies)], 0)
+    big_cell = cell.copy()
+    big_cell[axis, axis] *= copies
+    ei, sh = neighbor_list(big, big_cell, r_max)
+    return {
+        "pos": torch.from_numpy(big),
+        "cell": torch.from_numpy(big_cell),
+        "atom_types": data["atom_types"].repeat(copies),
+        "edge_index": torch.from_numpy(ei),
+        "edge_cell_shift": torch.from_numpy(sh),
+    }
+
+
 def to_device(data: Dict, device) -> Dict:
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}

@@ -115,3 +115,143 @@ def test_brick_decomposition():
     assert P.brick_grid(8, [374.0, 46.8, 46.8]) == (8, 1, 1)
     g = P.brick_grid(8, [93.6, 93.6, 93.6])
     assert g[0] * g[1] * g[2] == 8 and max(g) < 8
+
+
+def _worker_supercell(rank, world, port, full, n_base, f_base, e_base, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lengths = torch.diagonal(full["cell"]).tolist()
+        grid = P.brick_grid(world, lengths, halo=5.0)
+        owner = P.brick_owner(full["pos"], grid)
+        plan = P.make_plans(full["edge_index"], owner, world)[rank]
+        local = P.shard_data(full, plan)
+        halo = P.HaloExchange(plan, "cpu")
+        pos = local["pos"].clone().requires_grad_(True)
+        e_loc = _toy_energy(pos, local["atom_types"], local["edge_index"], local["cell"], local["edge_cell_shift"],
+                            plan.n_own, halo).sum()
+        (g,) = torch.autograd.grad(e_loc, pos)
+        e = e_loc.detach().reshape(1).clone()
+        dist.all_reduce(e)
+        f_own = -P.owner_reduce(g, plan, halo)
+        # bench.py's partition-parity check: owned atom g is a periodic copy of base atom g % n_base
+        err = (f_own - f_base[plan.owned % n_base]).abs().max().reshape(1)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ret["err"], ret["e"], ret["grid"] = float(err), float(e), grid
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_supercell_partition_reproduces_the_base_frame(world):
+    """bench.py's weak-scaling frame is the ``world``-fold periodic supercell of the N = 1 frame
+    (``data.replicate_frame``): sharded over ``world`` ranks it must give every copy of an atom the force of the
+    base atom in the unsharded base frame, and ``world`` times its energy."""
+    base = D.make_system("water", 6, r_max=5.0, seed=4)
+    base.pop("_meta")
+    n = base["pos"].shape[0]
+    full = D.replicate_frame(base, world, r_max=5.0)
+    assert full["pos"].shape[0] == world * n and full["edge_index"].shape[1] == world * base["edge_index"].shape[1]
+    assert torch.equal(full["atom_types"][n: 2 * n], base["atom_types"])
+    plan1 = P.make_plans(base["edge_index"], torch.zeros(n, dtype=torch.long), 1)[0]
+    pos = base["pos"].clone().requires_grad_(True)
+    e_base = _toy_energy(pos, base["atom_types"], base["edge_index"], base["cell"], base["edge_cell_shift"], n,
+                         P.HaloExchange(plan1, "cpu")).sum()
+    (g_base,) = torch.autograd.grad(e_base, pos)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_supercell, args=(world, _free_port(), full, n, -g_base.detach(), float(e_base), ret), nprocs=world, join=True)
+    assert ret["grid"] == (world, 1, 1)  # elongated along x -> slabs
+    assert ret["err"] < 1e-10 * float(g_base.abs().max())
+    assert abs(ret["e"] - world * float(e_base)) < 1e-10 * abs(world * float(e_base))
+
+
+def _load_bench():
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("nqb_bench_checks", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _toy_unsharded(frame):
+    """An 'unsharded model call' with the output keys of NequIPEnergyModel.forward, on the toy energy."""
+    n = frame["pos"].shape[0]
+    plan1 = P.make_plans(frame["edge_index"], torch.zeros(n, dtype=torch.long), 1)[0]
+    pos = frame["pos"].clone().requires_grad_(True)
+    e_atom = _toy_energy(pos, frame["atom_types"], frame["edge_index"], frame["cell"], frame["edge_cell_shift"], n,
+                         P.HaloExchange(plan1, "cpu"))
+    (g,) = torch.autograd.grad(e_atom.sum(), pos)
+    return {"forces": -g, "total_energy": e_atom.sum().detach().reshape(1, 1), "atomic_energy": e_atom.detach().reshape(-1, 1)}
+
+
+def _worker_checks(rank, world, port, full, base, copies, break_it, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bench = _load_bench()
+        grid = P.brick_grid(world, torch.diagonal(full["cell"]).tolist(), halo=5.0)
+        plan = P.make_plans(full["edge_index"], P.brick_owner(full["pos"], grid), world)[rank]
+        local = P.shard_data(full, plan)
+        halo = P.HaloExchange(plan, "cpu")
+
+        def step():  # what bench.py times in halo mode: sharded energy + owner-reduced forces
+            pos = local["pos"].clone().requires_grad_(True)
+            e_loc = _toy_energy(pos, local["atom_types"], local["edge_index"], local["cell"], local["edge_cell_shift"],
+                                plan.n_own, halo).sum()
+            (g,) = torch.autograd.grad(e_loc, pos)
+            e = e_loc.detach().reshape(1).clone()
+            dist.all_reduce(e)
+            f = -P.owner_reduce(g, plan, halo)
+            if break_it == 1 and rank == 1:
+                f = -g[: plan.n_own]  # a rank that forgets the ghost contributions it owes to / is owed by others
+            return {"total_energy": e, "forces": f}
+
+        model = _toy_unsharded
+        if break_it == 2 and rank == 0:
+            def model(frame):  # a rank whose local check blows up: reported, the collectives still line up
+                raise RuntimeError("boom")
+        checks = bench.parity_checks(step, model, base, copies, plan.owned, True, world, rank, torch.device("cpu"))
+        if rank == 0:
+            ret["checks"] = checks
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("break_it", [0, 1, 2])
+def test_bench_parity_checks_under_gloo(break_it):
+    """bench.py's ``parity_checks`` executed for real on 2 ranks (toy energy): green for a correct sharded step, a
+    dropped ghost contribution is flagged by both properties, and a rank whose local check raises is reported
+    without desynchronising the collectives."""
+    world = 2
+    base = D.make_system("water", 6, r_max=5.0, seed=4)
+    base.pop("_meta")
+    full = D.replicate_frame(base, world, r_max=5.0)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_checks, args=(world, _free_port(), full, base, world, break_it, ret), nprocs=world, join=True)
+    c = ret["checks"]
+    pp = c["partition_parity"]
+    assert c["ranks_reporting"] == world
+    if break_it == 0:
+        assert c["sum_forces_over_sum_abs_forces"] < 1e-12
+        assert pp["ranks_reporting"] == world and pp["max_dF_over_max_F"] < 1e-10 and pp["dE_over_sum_abs_Ei"] < 1e-12
+    elif break_it == 1:
+        assert c["sum_forces_over_sum_abs_forces"] > 1e-4 and pp["max_dF_over_max_F"] > 1e-3
+    else:
+        assert pp["ranks_reporting"] == world - 1 and pp["max_dF_over_max_F"] < 1e-10
+
+
+def test_bench_parity_checks_single_rank():
+    bench = _load_bench()
+    base = D.make_system("water", 5, r_max=5.0, seed=1)
+    base.pop("_meta")
+    c = bench.parity_checks(lambda: _toy_unsharded(base), None, None, 1, None, False, 1, 0, torch.device("cpu"))
+    assert "partition_parity" not in c and c["ranks_reporting"] == 1 and c["sum_forces_over_sum_abs_forces"] < 1e-12
