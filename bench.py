@@ -331,6 +331,59 @@ def parity_checks(step, unsharded_model, base_frame, copies, owned_ids, halo_mod
     return checks
 
 
+def halo_exchange_profile(dims, plan, halo, dev, world, reps=10):
+    """The data-path collective of the halo mode, timed alone: for every interaction layer >= 1 the forward exchange
+    (owned rows -> owned + ghost rows: index_select, all_to_all_single with split sizes into the tail of the feature
+    buffer) and forward + transposed backward (ghost gradients added into their owners), with feature rows of the
+    layer's width.  Every rank runs the same sequence of collectives; times are the max over ranks."""
+    import torch.distributed as dist
+
+    cuda = torch.device(dev).type == "cuda"
+
+    def sync():
+        if cuda:
+            torch.cuda.synchronize()
+
+    def timeit(fn):
+        fn()
+        sync()
+        if world > 1:
+            dist.barrier()
+        if cuda:  # device time (CUDA events on the launching stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            sync()
+            return e0.elapsed_time(e1) / reps
+        t0 = time.perf_counter()  # CPU / gloo (tests)
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    out = []
+    for li, d in dims:
+        x = torch.randn(plan.n_own, d, device=dev, dtype=torch.float32)
+        gy = torch.randn(plan.n_own + plan.n_ghost, d, device=dev, dtype=torch.float32)
+
+        def fwd():
+            return halo(x)
+
+        def fwd_bwd():
+            xr = x.detach().requires_grad_(True)
+            halo(xr).backward(gy)
+
+        t = torch.tensor([timeit(fwd), timeit(fwd_bwd)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = t.tolist()
+        out.append({"layer": li, "row_floats": d, "rows_sent": int(sum(plan.send_splits)), "rows_received": int(plan.n_ghost),
+                    "bytes_sent_per_exchange": int(sum(plan.send_splits)) * d * 4,
+                    "ms_forward": t[0], "ms_forward_plus_backward": t[1]})
+    return out
+
+
 def _time_cuda(fn, reps):
     for _ in range(3):
         fn()
@@ -682,6 +735,12 @@ def main():
     checks = parity_checks(step_resident, (lambda frame: model(D.to_device(frame, dev))), base_frame, copies,
                            (plan.owned if halo_mode else None), halo_mode, world, rank, dev)
 
+    # the collective of the data path, timed alone (halo mode): bytes and milliseconds per layer, max over ranks
+    exchange = None
+    if halo_mode:
+        dims = [(li, int(layer.conv.feature_irreps_in.dim)) for li, layer in enumerate(model.layers) if li > 0]
+        exchange = halo_exchange_profile(dims, plan, halo, dev, world)
+
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     d2h = f_host.numel() * 8 + 8
 
@@ -737,6 +796,13 @@ def main():
                 "note": "positions in, forces out; neighbour list (cell list) built on the GPU inside the timed region"}),
             "gpu_launches": launches,
             "checks": checks,
+            "halo_exchange": (None if exchange is None else {
+                "per_layer": exchange,
+                "ms_per_step_all_layers": sum(e["ms_forward_plus_backward"] for e in exchange),
+                "share_of_step": sum(e["ms_forward_plus_backward"] for e in exchange) / ms_res,
+                "note": ("the only data-path collective: per-layer all_to_all_single of the ghost rows (NCCL) and its transposed "
+                         "backward, timed alone with feature rows of each layer's width; plus one 8-byte energy all-reduce and "
+                         "one [n_ghost, 3] float64 reverse exchange of the ghost forces per step")}),
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -255,3 +255,35 @@ def test_bench_parity_checks_single_rank():
     base.pop("_meta")
     c = bench.parity_checks(lambda: _toy_unsharded(base), None, None, 1, None, False, 1, 0, torch.device("cpu"))
     assert "partition_parity" not in c and c["ranks_reporting"] == 1 and c["sum_forces_over_sum_abs_forces"] < 1e-12
+
+
+def _worker_exchange_profile(rank, world, port, full, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bench = _load_bench()
+        grid = P.brick_grid(world, torch.diagonal(full["cell"]).tolist(), halo=5.0)
+        plan = P.make_plans(full["edge_index"], P.brick_owner(full["pos"], grid), world)[rank]
+        prof = bench.halo_exchange_profile([(1, 12), (2, 40)], plan, P.HaloExchange(plan, "cpu"), "cpu", world, reps=2)
+        if rank == 0:
+            ret["prof"], ret["sent"], ret["ghost"] = prof, int(sum(plan.send_splits)), plan.n_ghost
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_bench_halo_exchange_profile_under_gloo():
+    """bench.py's timing of the data-path collective (per-layer halo exchange, forward and forward + backward)."""
+    base = D.make_system("water", 6, r_max=5.0, seed=4)
+    base.pop("_meta")
+    full = D.replicate_frame(base, 2, r_max=5.0)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_exchange_profile, args=(2, _free_port(), full, ret), nprocs=2, join=True)
+    prof = ret["prof"]
+    assert [p["layer"] for p in prof] == [1, 2] and [p["row_floats"] for p in prof] == [12, 40]
+    for p in prof:
+        assert p["rows_sent"] == ret["sent"] and p["rows_received"] == ret["ghost"]
+        assert p["bytes_sent_per_exchange"] == ret["sent"] * p["row_floats"] * 4
+        assert p["ms_forward"] > 0 and p["ms_forward_plus_backward"] > 0
