@@ -542,8 +542,8 @@ def main():
                          "per-layer NCCL halo exchange, energy all-reduce, ghost forces returned to their owners -- the "
                          "north_star partition; 'frames' = one independent frame per GPU (the reference's DDP axis)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="halo mode: 'weak' = the frame grows with N (N x the workload's atoms, box elongated along x); "
-                         "'strong' = the workload's own frame split N ways")
+                    help="halo mode: 'weak' = the frame grows with N (the N-fold periodic supercell of the workload's frame "
+                         "along x); 'strong' = the workload's own frame split N ways")
     ap.add_argument("--no-graph", action="store_true", help="eager step (no CUDA-graph replay)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one warm-up step, then ONE step between cudaProfilerStart/Stop (for ncu "
