@@ -317,13 +317,17 @@ def parity_checks(step, unsharded_model, base_frame, copies, owned_ids, halo_mod
         dist.all_reduce(ok_ranks)
         par[3] = ok_ranks[0]
     chk, par = chk.tolist(), par.tolist()
-    checks = {"sum_forces_over_sum_abs_forces": (math.sqrt(chk[0] ** 2 + chk[1] ** 2 + chk[2] ** 2) / chk[3]) if chk[3] > 0 else None,
+
+    def num(x):  # a NaN / inf must not make the JSON line unparsable
+        return x if (x is None or math.isfinite(x)) else repr(x)
+
+    checks = {"sum_forces_over_sum_abs_forces": num(math.sqrt(chk[0] ** 2 + chk[1] ** 2 + chk[2] ** 2) / chk[3]) if chk[3] > 0 else None,
               "ranks_reporting": int(round(chk[4])),
               "note": "Newton's third law over the whole frame (all ranks): a lost or doubled ghost contribution shows as ~1e-2"}
     if halo_mode:
         checks["partition_parity"] = {
-            "max_dF_over_max_F": (par[0] / par[1]) if par[1] > 0 else None,
-            "dE_over_sum_abs_Ei": par[2] if par[3] > 0 else None,
+            "max_dF_over_max_F": num(par[0] / par[1]) if par[1] > 0 else None,
+            "dE_over_sum_abs_Ei": num(par[2]) if par[3] > 0 else None,
             "ranks_reporting": int(round(par[3])),
             "what": (f"forces of every owned atom and the total energy of the frame sharded over {world} ranks vs the "
                      f"UNSHARDED {n_base}-atom base frame evaluated eagerly on each rank (the sharded frame is its "
@@ -749,10 +753,18 @@ def main():
     # headline `roofline`, the others are listed under `roofline.by_kernel`
     roof = None
     if rank == 0:
-        roof = kernel_rooflines(model, resident, n_atoms, n_edges, max(5, args.steps), ms_res, dev)
+        try:  # rank-local: a failure here must not cost the run its bench line
+            roof = kernel_rooflines(model, resident, n_atoms, n_edges, max(5, args.steps), ms_res, dev)
+        except Exception as exc:
+            roof = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            print(f"[bench] per-kernel rooflines failed: {roof['error']}", file=sys.stderr, flush=True)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
-        cpu = cpu_baseline(args.workload)
+        try:
+            cpu = cpu_baseline(args.workload)
+        except Exception as exc:
+            cpu = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            print(f"[bench] cpu_baseline failed: {cpu['error']}", file=sys.stderr, flush=True)
 
     if rank == 0:
         total_atoms = n_total_atoms if halo_mode else n_atoms * world
