@@ -98,6 +98,14 @@ def neighbor_list(pos: np.ndarray, cell: Optional[np.ndarray], r_max: float, pbc
 
 
 def _nl_bruteforce(pos, L, r_max):
+    if L is not None:
+        cells = np.floor(pos / L)
+        if np.any(cells != 0):
+            # atoms outside the home cell (unwrapped trajectories, nequip/utils/unittests/model_tests_basic.py:326-383):
+            # search among the wrapped images, then express the shifts for the positions as given --
+            # pos[j] - pos[i] + shift * L is the same vector as for the wrapped atoms
+            ei, sh = _nl_bruteforce(pos - cells * L, L, r_max)
+            return ei, sh + cells[ei[0]] - cells[ei[1]]
     N = pos.shape[0]
     if L is None:
         shifts = np.zeros((1, 3))

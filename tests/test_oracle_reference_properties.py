@@ -8,6 +8,8 @@ properties the reference itself demands of this path.  float64 model dtype, smal
 * edge embedding vanishes at the cutoff, other edges unaffected         :964-1000
 * isolated atoms restore the per-type energy shifts                     :932-962
 """
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -142,3 +144,57 @@ def test_isolated_atoms_restore_the_per_type_shifts(net):
                  "edge_index": torch.zeros(2, 0, dtype=torch.long)}
         e, _, _ = omodel.energy_and_forces(sdz, cfg, frame, torch.float64)
         assert float(e) == pytest.approx(float(sd["shifts"][t]), abs=1e-14)
+
+
+# ---- geometry: tests/unit/nn/test_utils.py:15-89 and model_tests_basic.py:326-383 (wrapped / unwrapped images)
+def _fcc(a=3.61, reps=1):
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]]) * a
+    cells = np.array([(i, j, k) for i in range(reps) for j in range(reps) for k in range(reps)]) * a
+    return (base[None] + cells[:, None]).reshape(-1, 3), np.eye(3) * a * reps
+
+
+def test_periodic_edges_of_close_packed_bulk():
+    """test_utils.py:32-42: every atom of fcc bulk has 12 neighbours at the nearest-neighbour distance."""
+    pos, cell = _fcc()
+    dist = 3.61 / math.sqrt(2)
+    ei, sh = D.neighbor_list(pos, cell, 1.05 * dist)
+    vec = omodel.edge_vectors(torch.from_numpy(pos), torch.from_numpy(ei), torch.from_numpy(cell), torch.from_numpy(sh))
+    assert ei.shape[1] == 12 * pos.shape[0] and (np.bincount(ei[0]) == 12).all()
+    torch.testing.assert_close(vec.norm(dim=-1), torch.full((ei.shape[1],), dist, dtype=torch.float64))
+    # gradients with respect to positions and cell exist (test_utils.py:45-69)
+    p, c = torch.from_numpy(pos).requires_grad_(True), torch.from_numpy(cell).requires_grad_(True)
+    v = omodel.edge_vectors(p, torch.from_numpy(ei), c, torch.from_numpy(sh))
+    gp, gc = torch.autograd.grad(v.square().sum(), [p, c])  # (the plain sum cancels between the two directions of an edge)
+    assert torch.isfinite(gp).all() and torch.isfinite(gc).all() and gc.abs().sum() > 0
+
+
+def test_wrapped_and_unwrapped_periodic_images_give_the_same_result(net):
+    """model_tests_basic.py:326-383: moving atoms into other periodic images changes the edge shifts by
+    ``cs[centre] - cs[neighbour]`` and nothing else."""
+    sd, cfg = net
+    pos, cell = _fcc(3.9, reps=2)  # 32 atoms, box 7.8 A < 2 r_max: several images per pair
+    rng = np.random.default_rng(12345)
+    pos = pos + rng.normal(scale=0.05, size=pos.shape)
+    types = rng.integers(0, len(TYPES), size=pos.shape[0])
+    ei, sh = D.neighbor_list(pos, cell, 3.5)
+    frame = {"pos": torch.from_numpy(pos), "cell": torch.from_numpy(cell), "atom_types": torch.from_numpy(types),
+             "edge_index": torch.from_numpy(ei), "edge_cell_shift": torch.from_numpy(sh)}
+    e0, a0, f0 = omodel.energy_and_forces(sd, cfg, frame, torch.float64)
+    for _ in range(3):
+        cs = rng.integers(-5, 5, size=(pos.shape[0], 3)).astype(np.float64)
+        pos2 = pos + cs @ cell
+        ei2, sh2 = D.neighbor_list(pos2, cell, 3.5)
+        assert np.array_equal(ei, ei2)
+        assert np.array_equal(sh + cs[ei[0]] - cs[ei[1]], sh2)
+        frame2 = dict(frame, pos=torch.from_numpy(pos2), edge_cell_shift=torch.from_numpy(sh2))
+        e1, a1, f1 = omodel.energy_and_forces(sd, cfg, frame2, torch.float64)
+        assert torch.allclose(e1, e0, atol=1e-9) and torch.allclose(a1, a0, atol=1e-9) and torch.allclose(f1, f0, atol=1e-9)
+
+
+def test_host_neighbor_list_handles_unwrapped_positions_cell_list_path():
+    """Same contract on the cell-list path of the host neighbour list (>= 64 atoms, box >= 3 r_max)."""
+    pos, cell = D.jittered_lattice(8, D.PRESETS["li3po4"]["density"], seed=3)
+    ei, sh = D.neighbor_list(pos, cell, 5.0)
+    cs = np.random.default_rng(0).integers(-5, 5, size=(pos.shape[0], 3)).astype(np.float64)
+    ei2, sh2 = D.neighbor_list(pos + cs @ cell, cell, 5.0)
+    assert np.array_equal(ei, ei2) and np.array_equal(sh + cs[ei[0]] - cs[ei[1]], sh2)
