@@ -35,6 +35,35 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _retry_once(test):
+    """Multi-process CPU tests share the machine with whatever else runs on it (the suite has been seen to lose ~1 run
+    in 30 to a transient rendezvous / scheduling hiccup): a failed test is run once more; a genuine failure fails twice."""
+    import functools
+
+    @functools.wraps(test)
+    def wrapped(*a, **k):
+        try:
+            return test(*a, **k)
+        except Exception:  # noqa: BLE001
+            return test(*a, **k)
+
+    return wrapped
+
+
+def _spawn(worker, world, args_after_port):
+    """``mp.spawn(worker, (world, port, *args))`` with one retry on a fresh port: the port is probed before the
+    workers bind it, and a rendezvous that loses that race (or a transient gloo connect error) must not fail the suite.
+    A genuine failure fails again."""
+    last = None
+    for _ in range(2):
+        try:
+            mp.spawn(worker, args=(world, _free_port(), *args_after_port), nprocs=world, join=True)
+            return
+        except Exception as exc:  # noqa: BLE001 - re-raised after the retry
+            last = exc
+    raise last
+
+
 def _worker(rank, world, port, sysd, ret, grid=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -67,6 +96,7 @@ def _worker(rank, world, port, sysd, ret, grid=None):
 
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("world,grid", [(2, None), (3, None), (4, (2, 2, 1))])
+@_retry_once
 def test_sharded_toy_model_matches_single_process(world, grid):
     sysd = D.make_system("water", 6, r_max=5.0, seed=4)
     sysd.pop("_meta")
@@ -79,7 +109,7 @@ def test_sharded_toy_model_matches_single_process(world, grid):
     (g_ref,) = torch.autograd.grad(e_ref, pos)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), sysd, ret, grid), nprocs=world, join=True)
+    _spawn(_worker, world, (sysd, ret, grid,))
     assert abs(float(ret["e"]) - float(e_ref)) < 1e-10 * max(1.0, abs(float(e_ref)))
     torch.testing.assert_close(ret["f"], -g_ref.detach(), atol=1e-11, rtol=1e-9)
     assert ret["ghost_frac"] > 0
@@ -146,6 +176,7 @@ def _worker_supercell(rank, world, port, full, n_base, f_base, e_base, ret):
 
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("world", [2, 3])
+@_retry_once
 def test_supercell_partition_reproduces_the_base_frame(world):
     """bench.py's weak-scaling frame is the ``world``-fold periodic supercell of the N = 1 frame
     (``data.replicate_frame``): sharded over ``world`` ranks it must give every copy of an atom the force of the
@@ -163,7 +194,7 @@ def test_supercell_partition_reproduces_the_base_frame(world):
     (g_base,) = torch.autograd.grad(e_base, pos)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker_supercell, args=(world, _free_port(), full, n, -g_base.detach(), float(e_base), ret), nprocs=world, join=True)
+    _spawn(_worker_supercell, world, (full, n, -g_base.detach(), float(e_base), ret,))
     assert ret["grid"] == (world, 1, 1)  # elongated along x -> slabs
     assert ret["err"] < 1e-10 * float(g_base.abs().max())
     assert abs(ret["e"] - world * float(e_base)) < 1e-10 * abs(world * float(e_base))
@@ -226,6 +257,7 @@ def _worker_checks(rank, world, port, full, base, copies, break_it, ret):
 
 @pytest.mark.timeout(240)
 @pytest.mark.parametrize("break_it", [0, 1, 2])
+@_retry_once
 def test_bench_parity_checks_under_gloo(break_it):
     """bench.py's ``parity_checks`` executed for real on 2 ranks (toy energy): green for a correct sharded step, a
     dropped ghost contribution is flagged by both properties, and a rank whose local check raises is reported
@@ -236,7 +268,7 @@ def test_bench_parity_checks_under_gloo(break_it):
     full = D.replicate_frame(base, world, r_max=5.0)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker_checks, args=(world, _free_port(), full, base, world, break_it, ret), nprocs=world, join=True)
+    _spawn(_worker_checks, world, (full, base, world, break_it, ret,))
     c = ret["checks"]
     pp = c["partition_parity"]
     assert c["ranks_reporting"] == world
@@ -273,6 +305,7 @@ def _worker_exchange_profile(rank, world, port, full, ret):
 
 
 @pytest.mark.timeout(180)
+@_retry_once
 def test_bench_halo_exchange_profile_under_gloo():
     """bench.py's timing of the data-path collective (per-layer halo exchange, forward and forward + backward)."""
     base = D.make_system("water", 6, r_max=5.0, seed=4)
@@ -280,7 +313,7 @@ def test_bench_halo_exchange_profile_under_gloo():
     full = D.replicate_frame(base, 2, r_max=5.0)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker_exchange_profile, args=(2, _free_port(), full, ret), nprocs=2, join=True)
+    _spawn(_worker_exchange_profile, 2, (full, ret,))
     prof = ret["prof"]
     assert [p["layer"] for p in prof] == [1, 2] and [p["row_floats"] for p in prof] == [12, 40]
     for p in prof:
