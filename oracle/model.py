@@ -224,6 +224,10 @@ def energy(sd: Dict[str, torch.Tensor], cfg: dict, data: dict, model_dtype=torch
         e_atom = e_atom * sd["scales"][types]
     if "shifts" in sd and sd["shifts"].numel():
         e_atom = e_atom + sd["shifts"][types]
+    if data.get("batch") is not None:  # AtomwiseReduce per graph (nequip/nn/atomwise.py:92-113): [num_graphs, 1]
+        batch = data["batch"].view(-1).long()
+        ng = int(data["num_atoms"].numel()) if "num_atoms" in data else (int(batch.max()) + 1 if batch.numel() else 0)
+        return torch.zeros((ng, 1), dtype=e_atom.dtype).index_add(0, batch, e_atom), e_atom
     return e_atom.sum(0, keepdim=True), e_atom
 
 

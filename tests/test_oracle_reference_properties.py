@@ -198,3 +198,30 @@ def test_host_neighbor_list_handles_unwrapped_positions_cell_list_path():
     cs = np.random.default_rng(0).integers(-5, 5, size=(pos.shape[0], 3)).astype(np.float64)
     ei2, sh2 = D.neighbor_list(pos + cs @ cell, cell, 5.0)
     assert np.array_equal(ei, ei2) and np.array_equal(sh + cs[ei[0]] - cs[ei[1]], sh2)
+
+
+def test_batched_frames_equal_the_frames_evaluated_one_by_one(net):
+    """model_tests_basic.py:385-448 (``test_batch``) and :598-629 (cross-frame gradient isolation): graph fields per
+    frame, node fields per atom, and no force leaks from one frame of a batch into another."""
+    sd, cfg = net
+    frames = [_frame(*_cluster(n, seed)) for n, seed in ((6, 21), (9, 22), (1, 23))]
+    outs = [omodel.energy_and_forces(sd, cfg, f, torch.float64) for f in frames]
+    off = np.cumsum([0] + [f["pos"].shape[0] for f in frames])
+    batched = {
+        "pos": torch.cat([f["pos"] for f in frames]),
+        "atom_types": torch.cat([f["atom_types"] for f in frames]),
+        "edge_index": torch.cat([f["edge_index"] + int(o) for f, o in zip(frames, off)], dim=1),
+        "batch": torch.cat([torch.full((f["pos"].shape[0],), i) for i, f in enumerate(frames)]),
+        "num_atoms": torch.tensor([f["pos"].shape[0] for f in frames]),
+    }
+    e, a, f = omodel.energy_and_forces(sd, cfg, batched, torch.float64)
+    assert e.shape == (3, 1)
+    for i, (ei, ai, fi) in enumerate(outs):
+        sl = slice(int(off[i]), int(off[i + 1]))
+        assert torch.allclose(e[i], ei.view(-1), atol=1e-10)
+        assert torch.allclose(a[sl], ai, atol=1e-10) and torch.allclose(f[sl], fi, atol=1e-10)
+    # cross-frame isolation: the energy of frame 0 has no gradient on the atoms of the other frames
+    pos = batched["pos"].clone().requires_grad_(True)
+    e_tot, _ = omodel.energy(sd, cfg, dict(batched, pos=pos), torch.float64)
+    (g0,) = torch.autograd.grad(e_tot[0].sum(), pos)
+    assert g0[: int(off[1])].abs().sum() > 0 and float(g0[int(off[1]):].abs().max()) == 0.0
