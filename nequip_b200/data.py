@@ -42,6 +42,12 @@ def neighbor_list(pos: np.ndarray, cell: Optional[np.ndarray], r_max: float, pbc
     """Full neighbour list within r_max.  Orthorhombic cells only.  Returns
     (edge_index [2,E] int64, shifts [E,3] float64) sorted by (centre, neighbour)."""
     N = pos.shape[0]
+    if not isinstance(pbc, (bool, np.bool_)):  # per-direction flags (mixed boundary conditions, e.g. a slab)
+        flags = [bool(b) for b in pbc]
+        if cell is not None and any(flags) and not all(flags):
+            assert np.allclose(cell, np.diag(np.diag(cell))), "orthorhombic cells only"
+            return _nl_bruteforce(pos, np.diag(cell).copy(), r_max, periodic=np.array(flags))
+        pbc = all(flags)
     if cell is None or not pbc:
         L = None
     else:
@@ -97,7 +103,30 @@ def neighbor_list(pos: np.ndarray, cell: Optional[np.ndarray], r_max: float, pbc
     return np.stack([ii[o], jj[o]]).astype(np.int64), sh[o]
 
 
-def _nl_bruteforce(pos, L, r_max):
+def _nl_bruteforce(pos, L, r_max, periodic=None):
+    """``periodic`` (optional bool[3]): directions without periodic images (their cell length is ignored)."""
+    if L is not None and periodic is not None:
+        per = np.asarray(periodic, dtype=bool)
+        Lp = np.where(per, L, 1.0)
+        cells = np.where(per, np.floor(pos / Lp), 0.0)  # wrap along the periodic directions only
+        w = pos - cells * Lp
+        reps = np.where(per, np.ceil(r_max / Lp), 0).astype(int)
+        rng = [np.arange(-r, r + 1) for r in reps]
+        shifts = np.array([(a, b, c) for a in rng[0] for b in rng[1] for c in rng[2]], dtype=np.float64)
+        ii, jj, ss = [], [], []
+        for s in shifts:
+            d = w[None, :, :] + s * Lp - w[:, None, :]
+            ok = (d * d).sum(-1) < r_max * r_max
+            if not np.any(s):
+                ok &= ~np.eye(pos.shape[0], dtype=bool)
+            i, j = np.nonzero(ok)
+            ii.append(i)
+            jj.append(j)
+            ss.append(np.broadcast_to(s, (i.size, 3)))
+        ii, jj, ss = np.concatenate(ii), np.concatenate(jj), np.concatenate(ss).astype(np.float64)
+        o = np.lexsort((jj, ii))
+        ei = np.stack([ii[o], jj[o]]).astype(np.int64)
+        return ei, ss[o] + cells[ei[0]] - cells[ei[1]]
     if L is not None:
         cells = np.floor(pos / L)
         if np.any(cells != 0):

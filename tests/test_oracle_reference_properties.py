@@ -225,3 +225,24 @@ def test_batched_frames_equal_the_frames_evaluated_one_by_one(net):
     e_tot, _ = omodel.energy(sd, cfg, dict(batched, pos=pos), torch.float64)
     (g0,) = torch.autograd.grad(e_tot[0].sum(), pos)
     assert g0[: int(off[1])].abs().sum() > 0 and float(g0[int(off[1]):].abs().max()) == 0.0
+
+
+def test_mixed_boundary_conditions_monolayer():
+    """test_utils.py:72-95 (``test_some_periodic``): an fcc(111) monolayer periodic in x and y only -- every atom has
+    its 6 in-plane first-shell neighbours and no edge has a z component (no images across the vacuum)."""
+    a_nn = 2.864  # Al first-shell distance
+    # orthorhombic 2-atom cell of the triangular lattice, 3 x 2 cells, 20 A of vacuum along z
+    base = np.array([[0.0, 0.0, 10.0], [0.5 * a_nn, 0.5 * math.sqrt(3) * a_nn, 10.0]])
+    pos = np.concatenate([base + np.array([i * a_nn, j * math.sqrt(3) * a_nn, 0.0]) for i in range(3) for j in range(2)])
+    cell = np.diag([3 * a_nn, 2 * math.sqrt(3) * a_nn, 20.0])
+    ei, sh = D.neighbor_list(pos, cell, 2.9, pbc=(True, True, False))
+    assert (np.bincount(ei[0], minlength=pos.shape[0]) == 6).all()
+    vec = omodel.edge_vectors(torch.from_numpy(pos), torch.from_numpy(ei), torch.from_numpy(cell), torch.from_numpy(sh))
+    torch.testing.assert_close(vec[:, 2], torch.zeros(ei.shape[1], dtype=torch.float64))
+    torch.testing.assert_close(vec.norm(dim=-1), torch.full((ei.shape[1],), a_nn, dtype=torch.float64))
+    assert (sh[:, 2] == 0).all()
+    # fully periodic with a z length below r_max would add images across z: the flags matter
+    thin = np.diag([3 * a_nn, 2 * math.sqrt(3) * a_nn, 2.5])
+    ei_z, _ = D.neighbor_list(pos, thin, 2.9, pbc=True)
+    ei_slab, _ = D.neighbor_list(pos, thin, 2.9, pbc=(True, True, False))
+    assert ei_z.shape[1] > ei_slab.shape[1] == ei.shape[1]
